@@ -1,0 +1,194 @@
+"""Parity cases shared by the pin script, the oracle tests and the GPU parity tests
+-- TEST INFRASTRUCTURE (see oracle/ies_oracle.py header).
+
+A case is a plain dict.  `run_api(ns, case, engine)` drives any implementation
+that exposes the reference's Python API (the reference itself via
+oracle/ref_shims.py, or the product package ies_b200); `run_oracle(case)`
+drives the NumPy restatement.  Both return {field name: ndarray} of the global
+fields after `steps` steps (slabs concatenated along x).
+"""
+from __future__ import annotations
+
+import numpy as np
+from scipy.constants import c
+
+um = 1e-6
+FIELDS = ('Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz')
+
+
+def _case(name, method, dtype, grid, steps=30, pml=None, npml=4, bbc=None, pbc=None,
+          mmt=(0., 0., 0.), ranks=1, src='plane', src_field='Ey', boxes=True, put='soft',
+          pulse=None, mmtdtype=None, golden=None):
+    dtype = np.dtype(dtype)
+    cplx = dtype.kind == 'c'
+    if mmtdtype is None:
+        mmtdtype = np.complex128 if dtype in (np.dtype('float64'), np.dtype('complex128')) else np.complex64
+    return dict(name=name, method=method, dtype=dtype.name, mmtdtype=np.dtype(mmtdtype).name,
+                grid=tuple(grid), steps=steps,
+                pml=pml if pml is not None else {'x': '+-', 'y': '', 'z': ''}, npml=npml,
+                bbc=bbc, pbc=pbc, mmt=tuple(mmt), ranks=ranks, src=src, src_field=src_field,
+                boxes=boxes, put=put, pulse=pulse or ('c' if cplx else 're'),
+                golden=golden or name)
+
+
+ALLPML = {'x': '+-', 'y': '+-', 'z': '+-'}
+NOPML = {'x': '', 'y': '', 'z': ''}
+PBC_YZ = {'x': False, 'y': True, 'z': True}
+BBC_YZ = {'x': False, 'y': True, 'z': True}
+BBC_ALL = {'x': True, 'y': True, 'z': True}
+NO = {'x': False, 'y': False, 'z': False}
+K1 = (0., 2 * np.pi / (512 * um) * 0.3, 2 * np.pi / (512 * um) * 0.2)
+K3 = (2 * np.pi / (720 * um) * 0.25, 2 * np.pi / (512 * um) * 0.3, 2 * np.pi / (512 * um) * 0.2)
+
+CASES = [
+    _case('shpf_f64_xpml', 'SHPF', 'float64', (32, 16, 16), pbc=PBC_YZ, bbc=NO),
+    _case('shpf_f32_xpml', 'SHPF', 'float32', (32, 16, 16), pbc=PBC_YZ, bbc=NO),
+    _case('shpf_c64_xpml', 'SHPF', 'complex64', (32, 16, 32), pbc=PBC_YZ, bbc=NO),
+    _case('shpf_c128_bloch_yz', 'SHPF', 'complex128', (32, 16, 16), bbc=BBC_YZ, pbc=NO, mmt=K1, src='point'),
+    _case('shpf_f64_allpml', 'SHPF', 'float64', (32, 32, 16), pml=ALLPML, src='point'),
+    _case('shpf_f64_allpml_r2', 'SHPF', 'float64', (32, 32, 16), pml=ALLPML, src='point', ranks=2, golden='shpf_f64_allpml'),
+    _case('shpf_f64_xpml_r4', 'SHPF', 'float64', (32, 16, 16), pbc=PBC_YZ, bbc=NO, ranks=4, golden='shpf_f64_xpml'),
+    _case('shpf_f64_ypml_only', 'SHPF', 'float64', (16, 32, 16), pml={'x': '', 'y': '+', 'z': '-'}, src='point'),
+    _case('fdtd_f64_xpml_pbc', 'FDTD', 'float64', (32, 20, 18), pbc=PBC_YZ, bbc=NO),
+    _case('fdtd_f32_xpml_pbc', 'FDTD', 'float32', (32, 20, 18), pbc=PBC_YZ, bbc=NO),
+    _case('fdtd_c64_xpml_pbc', 'FDTD', 'complex64', (32, 20, 30), pbc=PBC_YZ, bbc=NO),
+    _case('fdtd_c128_bloch_yz', 'FDTD', 'complex128', (32, 20, 18), bbc=BBC_YZ, pbc=NO, mmt=K1, src='point'),
+    _case('fdtd_f64_allpml', 'FDTD', 'float64', (30, 28, 26), pml=ALLPML, bbc=NO, pbc=NO, src='point'),
+    _case('fdtd_f64_allpml_r2', 'FDTD', 'float64', (30, 28, 26), pml=ALLPML, bbc=NO, pbc=NO, src='point', ranks=2),
+    _case('fdtd_f64_xpml_pbc_r4', 'FDTD', 'float64', (32, 20, 18), pbc=PBC_YZ, bbc=NO, ranks=4, golden='fdtd_f64_xpml_pbc'),
+    _case('fdtd_c128_pbcx', 'FDTD', 'complex128', (24, 20, 18), pml=NOPML, pbc={'x': True, 'y': True, 'z': True}, bbc=NO, src='point'),
+    _case('pstd_c128_bloch_all', 'PSTD', 'complex128', (16, 16, 16), pml=NOPML, bbc=BBC_ALL, pbc=NO, mmt=K3, src='point', boxes=True),
+    _case('pstd_f64_allpml', 'PSTD', 'float64', (32, 32, 16), pml=ALLPML, src='point'),
+    _case('pstd_c64_xpml', 'PSTD', 'complex64', (32, 16, 16), src='plane'),
+    _case('pstd_f64_nopml_hard', 'PSTD', 'float64', (16, 16, 32), pml=NOPML, src='point', put='hard'),
+]
+CASES_BY_NAME = {k['name']: k for k in CASES}
+
+
+def geometry(case):
+    Nx, Ny, Nz = case['grid']
+    Lx, Ly, Lz = 720 * um, 512 * um, 512 * um
+    dx, dy, dz = Lx / Nx, Ly / Ny, Lz / Nz
+    dt = 0.25 * min(dx, dy, dz) / c
+    return (Lx, Ly, Lz), (dx, dy, dz), dt
+
+
+def source_box(case):
+    (Lx, Ly, Lz), (dx, dy, dz), dt = geometry(case)
+    if case['src'] == 'plane':
+        xs = Lx * 0.3
+        return (xs, 0, 0), (xs, Ly, Lz)
+    # point dipole (src_end = src_srt + one cell, source.py docstring case 2)
+    xs, ys, zs = Lx * 0.4, Ly * 0.45, Lz * 0.55
+    return (xs, ys, zs), (xs + dx, ys + dy, zs + dz)
+
+
+def pulse_value(case, step, dt):
+    """Gaussian pulse (source.py:278-290) with a short rise so 30 steps see it."""
+    wvc, spread, peak = 100 * um, 0.3, 12
+    w0 = 2 * np.pi * (c / wvc)
+    ws = spread * w0
+    tc = peak * dt
+    env = np.exp((-.5) * (((step * dt - tc) * ws) ** 2))
+    if case['pulse'] == 'c':
+        return env * np.exp(-1j * w0 * (step * dt - tc))
+    return env * np.cos(w0 * (step * dt - tc))
+
+
+def box_list(case):
+    (Lx, Ly, Lz), d, dt = geometry(case)
+    if not case['boxes']:
+        return []
+    return [((Lx * 0.5, 0, 0), (Lx * 0.65, Ly, Lz), 4., 1.),
+            ((Lx * 0.7, Ly * 0.25, Lz * 0.25), (Lx * 0.8, Ly * 0.75, Lz * 0.6), 2.25, 1.5)]
+
+
+# ------------------------------------------------------------------ API runner
+def build_api(ns, case, engine):
+    """Build (space, setter) with the reference's API (tutorials/RT_simple_slabs.py:55-249)."""
+    (Lx, Ly, Lz), gap, dt = geometry(case)
+    fd = np.dtype(case['dtype']).type
+    md = np.dtype(case['mmtdtype']).type
+    sp = ns.space.Basic3D(case['grid'], gap, dt, case['steps'] + 1, fd, md,
+                          method=case['method'], engine=engine)
+    sp.malloc()
+    sp.apply_PML(case['pml'], case['npml'])
+    if case['bbc'] is not None:
+        sp.apply_BBC(case['bbc'])
+    if case['pbc'] is not None:
+        sp.apply_PBC(case['pbc'])
+    s0, s1 = source_box(case)
+    setter = ns.source.Setter(sp, s0, s1, case['mmt'])
+    for (b0, b1, er, mr) in box_list(case):
+        ns.structure.Box('box', sp, b0, b1, er, mr)
+    sp.init_update_constants()
+    return sp, setter
+
+
+def step_api(sp, setter, case, t):
+    setter.put_src(case['src_field'], pulse_value(case, t, sp.dt), case['put'])
+    sp.updateH(t)
+    sp.updateE(t)
+
+
+def run_api(ns, case, engine, to_numpy=np.asarray):
+    """Single-rank run through the reference-style API."""
+    assert case['ranks'] == 1
+    sp, setter = build_api(ns, case, engine)
+    for t in range(case['steps']):
+        step_api(sp, setter, case, t)
+    return {n: to_numpy(getattr(sp, n)[:, :, :]) for n in FIELDS}
+
+
+# --------------------------------------------------------------- oracle runner
+def build_oracle(case):
+    from . import ies_oracle as O
+    (Lx, Ly, Lz), gap, dt = geometry(case)
+    cl = O.OracleCluster(case['ranks'], case['grid'], gap, dt, case['steps'] + 1,
+                         np.dtype(case['dtype']).type, np.dtype(case['mmtdtype']).type,
+                         method=case['method'])
+    s0, s1 = source_box(case)
+    setters = []
+    for sp in cl.slabs:
+        sp.apply_PML(case['pml'], case['npml'])
+        if case['bbc'] is not None:
+            sp.apply_BBC(case['bbc'])
+        if case['pbc'] is not None:
+            sp.apply_PBC(case['pbc'])
+        setters.append(O.OracleSetter(sp, s0, s1, case['mmt']))
+        for (b0, b1, er, mr) in box_list(case):
+            oracle_box(sp, b0, b1, er, mr)
+        sp.init_update_constants()
+    return cl, setters
+
+
+def oracle_box(sp, srt, end, eps_r, mu_r):
+    """structure.Box (structure.py:108-192) + Structure._get_local_x_loc (17-107)."""
+    from . import ies_oracle as O
+    from scipy.constants import epsilon_0, mu_0
+    xs, ys, zs = (round(srt[0] / sp.dx), round(srt[1] / sp.dy), round(srt[2] / sp.dz))
+    xe, ye, ze = (round(end[0] / sp.dx), round(end[1] / sp.dy), round(end[2] / sp.dz))
+    assert xs < xe and ys < ye and zs < ze
+    g, l = O.local_x_loc(sp, xs, xe)
+    if g is not None:
+        sp.eps[l[0]:l[1], ys:ye, zs:ze] = eps_r * epsilon_0
+        sp.mu[l[0]:l[1], ys:ye, zs:ze] = mu_r * mu_0
+
+
+def run_oracle(case):
+    cl, setters = build_oracle(case)
+    dt = cl.slabs[0].dt
+    for t in range(case['steps']):
+        p = pulse_value(case, t, dt)
+        for s in setters:
+            s.put_src(case['src_field'], p, case['put'])
+        cl.update_h(t)
+        cl.update_e(t)
+    return {n: cl.gather(n) for n in FIELDS}
+
+
+def rel_l2(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    den = np.linalg.norm(b.ravel())
+    num = np.linalg.norm((a - b).ravel())
+    return float(num / den) if den > 0 else float(num)
