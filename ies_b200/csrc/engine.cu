@@ -1,0 +1,741 @@
+// libies_b200.so -- C-ABI host layer + the non-spectral kernels (FDTD update,
+// ghost-plane copies, source injection, collectors, field pack/unpack).
+// See include/ies_b200.h for the reference lines each entry point replaces.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <algorithm>
+
+#include "engine.h"
+#include "update_dev.cuh"
+
+namespace ies {
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+void set_error(const std::string& s) { g_err = s; }
+void count_launch(int n) { g_launches += n; }
+bool fft_len_supported(int n) { return n >= 16 && n <= 512 && (n & (n - 1)) == 0; }
+
+// ------------------------------------------------------------------ FDTD -----
+// Yee curl with two-point differences (space.py:760-779, 975-994) + the fused
+// update/CPML of update_dev.cuh.  One thread per cell, z fastest (coalesced).
+template <typename T, bool CPLX>
+__global__ void __launch_bounds__(256) k_fdtd(const UpdParams p) {
+    using A = typename AccT<CPLX>::type;
+    using E = Elem<T, CPLX>;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = blockIdx.y * blockDim.y + threadIdx.y;
+    const int i = p.i0 + blockIdx.z;
+    if (k >= p.nz || j >= p.ny) return;
+    const size_t plane = (size_t)p.ny * p.nz;
+    const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
+    const int dir = p.dir;
+    A d[6];
+    const A fx = E::ld(p.F[0], idx), fy = E::ld(p.F[1], idx), fz = E::ld(p.F[2], idx);
+    // y neighbour
+    const int jn = j + dir, kn = k + dir, in = i + dir;
+    const double sy = dir > 0 ? p.rdy : -p.rdy, sz = dir > 0 ? p.rdz : -p.rdz, sx = dir > 0 ? p.rdx : -p.rdx;
+    if (jn >= 0 && jn < p.ny) {
+        const size_t n = idx + (ptrdiff_t)dir * p.nz;
+        d[0] = a_scale(sy, a_sub(E::ld(p.F[2], n), fz));
+        d[5] = a_scale(sy, a_sub(E::ld(p.F[0], n), fx));
+    } else { d[0] = a_zero(A()); d[5] = a_zero(A()); }
+    if (kn >= 0 && kn < p.nz) {
+        const size_t n = idx + (ptrdiff_t)dir;
+        d[1] = a_scale(sz, a_sub(E::ld(p.F[1], n), fy));
+        d[2] = a_scale(sz, a_sub(E::ld(p.F[0], n), fx));
+    } else { d[1] = a_zero(A()); d[2] = a_zero(A()); }
+    if (in >= 0 && in < p.nx) {
+        const size_t n = idx + (ptrdiff_t)dir * plane;
+        d[3] = a_scale(sx, a_sub(E::ld(p.F[2], n), fz));
+        d[4] = a_scale(sx, a_sub(E::ld(p.F[1], n), fy));
+    } else if (p.halo[0] != nullptr) {
+        const size_t n = (size_t)j * p.nz + k;
+        d[3] = a_scale(sx, a_sub(E::ld(p.halo[1], n), fz));
+        d[4] = a_scale(sx, a_sub(E::ld(p.halo[0], n), fy));
+    } else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
+    const unsigned mask = p.nterms ? ((1u << p.nterms) - 1u) : 0u;
+    cell_update<T, CPLX>(p, mask, i, j, k, d);
+}
+
+// Ghost-plane copies F[-1] = F[1]*pp ; F[0] = F[-2]*pm along `axis` for the three
+// components, and for the two halo planes along y/z (space.py:1714-1796).
+template <typename T, bool CPLX>
+__global__ void k_ghost(void* f0, void* f1, void* f2, void* h0, void* h1, int nx, int ny, int nz,
+                        int axis, double2 pp, double2 pm) {
+    using A = typename AccT<CPLX>::type;
+    using E = Elem<T, CPLX>;
+    const int na = axis == 0 ? ny : nx, nb = axis == 2 ? ny : nz;   // the two other extents
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long per = (long)na * nb;
+    auto mulp = [](A v, double2 ph) -> A {
+        if constexpr (CPLX) return make_double2(v.x * ph.x - v.y * ph.y, v.x * ph.y + v.y * ph.x);
+        else return v * ph.x;
+    };
+    if (tid < per * 3) {
+        const int comp = (int)(tid / per);
+        const long r = tid % per;
+        const int a = (int)(r / nb), b = (int)(r % nb);
+        void* f = comp == 0 ? f0 : comp == 1 ? f1 : f2;
+        auto at = [&](int s) -> size_t {
+            int i = axis == 0 ? s : a;
+            int j = axis == 1 ? s : (axis == 0 ? a : b);
+            int k = axis == 2 ? s : b;
+            return ((size_t)i * ny + j) * nz + k;
+        };
+        const int N = axis == 0 ? nx : axis == 1 ? ny : nz;
+        E::st(f, at(N - 1), mulp(E::ld(f, at(1)), pp));
+        E::st(f, at(0), mulp(E::ld(f, at(N - 2)), pm));
+    } else if (h0 != nullptr && axis > 0) {
+        // halo planes are (ny, nz); patch along y (axis 1) or z (axis 2)
+        const long r = tid - per * 3;
+        const int other = axis == 1 ? nz : ny;
+        if (r < 2L * other) {
+            void* h = r < other ? h0 : h1;
+            const int o = (int)(r % other);
+            auto at = [&](int s) -> size_t { return axis == 1 ? (size_t)s * nz + o : (size_t)o * nz + s; };
+            const int N = axis == 1 ? ny : nz;
+            E::st(h, at(N - 1), mulp(E::ld(h, at(1)), pp));
+            E::st(h, at(0), mulp(E::ld(h, at(N - 2)), pm));
+        }
+    }
+}
+
+// Setter.put_src (source.py:167-253)
+template <typename T, bool CPLX>
+__global__ void k_put_src(void* f, int ny, int nz, Box bx, double2 pulse, int hard,
+                          const double2* px, const double2* py, const double2* pz) {
+    using A = typename AccT<CPLX>::type;
+    using E = Elem<T, CPLX>;
+    const int ex = bx.hi[0] - bx.lo[0], ey = bx.hi[1] - bx.lo[1], ez = bx.hi[2] - bx.lo[2];
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (long)ex * ey * ez) return;
+    const int c = (int)(tid % ez), b = (int)((tid / ez) % ey), a = (int)(tid / ((long)ez * ey));
+    double vr = pulse.x, vi = pulse.y;
+    if (px) {
+        // pulse * ((px*py)*pz), the product order of source.py:231-232
+        const double2 X = px[a], Y = py[b], Z = pz[c];
+        const double tr = X.x * Y.x - X.y * Y.y, ti = X.x * Y.y + X.y * Y.x;
+        const double ur = tr * Z.x - ti * Z.y, ui = tr * Z.y + ti * Z.x;
+        const double wr = vr * ur - vi * ui, wi = vr * ui + vi * ur;
+        vr = wr; vi = wi;
+    }
+    const size_t idx = ((size_t)(bx.lo[0] + a) * ny + (bx.lo[1] + b)) * nz + (bx.lo[2] + c);
+    A add;
+    if constexpr (CPLX) add = make_double2(vr, vi); else add = vr;
+    if (hard) E::st(f, idx, add);
+    else E::st(f, idx, a_add(E::ld(f, idx), add));
+}
+
+// pack / unpack a box for ies_get_field / ies_set_field
+template <typename S>
+__global__ void k_pack(const S* f, S* out, int ny, int nz, Box bx, int unpack) {
+    const int ex = bx.hi[0] - bx.lo[0], ey = bx.hi[1] - bx.lo[1], ez = bx.hi[2] - bx.lo[2];
+    const long n = (long)ex * ey * ez;
+    for (long tid = (long)blockIdx.x * blockDim.x + threadIdx.x; tid < n; tid += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(tid % ez), b = (int)((tid / ez) % ey), a = (int)(tid / ((long)ez * ey));
+        const size_t idx = ((size_t)(bx.lo[0] + a) * ny + (bx.lo[1] + b)) * nz + (bx.lo[2] + c);
+        if (unpack) const_cast<S*>(f)[idx] = out[tid]; else out[tid] = f[idx];
+    }
+}
+
+// ------------------------------------------------------------- collectors -----
+struct DftDev {
+    double2* acc[4];
+    int nf;
+    long ncell;
+};
+
+// phase[f] = exp(2 pi i f t dt) * dt with the operand order of collector.py:334
+__global__ void k_dft_phase(const double* freqs, int nf, double tstep, double dt, double2* phase) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nf) return;
+    const double arg = ((2.0 * 3.141592653589793) * freqs[f]) * tstep * dt;
+    double s, c;
+    sincos(arg, &s, &c);
+    phase[f] = make_double2(c, s);
+}
+
+template <typename T, bool CPLX>
+__global__ void __launch_bounds__(256)
+k_dft_acc(DftDev d, const void* a0, const void* a1, const void* a2, const void* a3,
+          const void* b0, const void* b1, const void* b2, const void* b3,
+          int ny, int nz, Box bx, const double2* __restrict__ phase, double dt) {
+    using E = Elem<T, CPLX>;
+    const int ey = bx.hi[1] - bx.lo[1], ez = bx.hi[2] - bx.lo[2];
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= d.ncell) return;
+    const int c = (int)(tid % ez), b = (int)((tid / ez) % ey), a = (int)(tid / ((long)ez * ey));
+    const size_t idx = ((size_t)(bx.lo[0] + a) * ny + (bx.lo[1] + b)) * nz + (bx.lo[2] + c);
+    const void* fa[4] = {a0, a1, a2, a3};
+    const void* fb[4] = {b0, b1, b2, b3};
+    double2 v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        auto x = E::ld(fa[q], idx);
+        if (fb[q]) {
+            // Empty3D.get_SF: SF = TF - IF, evaluated in field precision (space.py:2173-2179)
+            x = E::rnd(a_sub(x, E::ld(fb[q], idx)));
+        }
+        if constexpr (CPLX) v[q] = x; else v[q] = make_double2(x, 0.0);
+    }
+    for (int f = 0; f < d.nf; ++f) {
+        const double2 ph = phase[f];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            double2* acc = d.acc[q] + (size_t)f * d.ncell + tid;
+            double2 s = *acc;
+            // (F * exp(..)) * dt
+            double re, im;
+            if constexpr (CPLX) { re = v[q].x * ph.x - v[q].y * ph.y; im = v[q].x * ph.y + v[q].y * ph.x; }
+            else { re = v[q].x * ph.x; im = v[q].x * ph.y; }
+            s.x += re * dt; s.y += im * dt;
+            *acc = s;
+        }
+    }
+}
+
+template <typename T, bool CPLX>
+__global__ void k_probe(void* out, long tsteps, long tstep, const void* a0, const void* a1, const void* a2,
+                        const void* a3, const void* a4, const void* a5, const void* b0, const void* b1,
+                        const void* b2, const void* b3, const void* b4, const void* b5, size_t idx) {
+    using E = Elem<T, CPLX>;
+    const int q = threadIdx.x;
+    if (q >= 6) return;
+    const void* fa[6] = {a0, a1, a2, a3, a4, a5};
+    const void* fb[6] = {b0, b1, b2, b3, b4, b5};
+    auto x = E::ld(fa[q], idx);
+    if (fb[q]) x = a_sub(x, E::ld(fb[q], idx));
+    E::st(out, (size_t)q * tsteps + tstep, x);
+}
+
+}  // namespace ies
+
+// =============================================================== C ABI =======
+using namespace ies;
+
+struct ies_ctx : public Ctx {};
+struct ies_dft {
+    ies_ctx* ctx;
+    Box box;
+    int comps[4];
+    int nf;
+    long ncell;
+    double2* acc[4];
+    double* freqs;
+    double2* phase;
+};
+struct ies_probe {
+    ies_ctx* ctx;
+    size_t idx;
+    long tsteps;
+    void* buf;
+};
+
+#define DISPATCH(ctx, ...)                                             \
+    switch ((ctx)->cfg.dtype) {                                         \
+        case IES_F32:  { using T = float;  constexpr bool CP = false; __VA_ARGS__; } break;  \
+        case IES_F64:  { using T = double; constexpr bool CP = false; __VA_ARGS__; } break;  \
+        case IES_C64:  { using T = float;  constexpr bool CP = true;  __VA_ARGS__; } break;  \
+        case IES_C128: { using T = double; constexpr bool CP = true;  __VA_ARGS__; } break;  \
+        default: set_error("bad dtype"); return 1;                      \
+    }
+
+static int dev_alloc(Ctx* c, void** p, size_t bytes, bool zero = true) {
+    IES_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+    c->owned.push_back(*p);
+    if (zero) IES_CUDA(cudaMemsetAsync(*p, 0, bytes, c->stream));
+    return 0;
+}
+
+static int fill_params(ies_ctx* c, int half, UpdParams& p) {
+    const int fo = half == IES_HALF_H ? 0 : 3, go = half == IES_HALF_H ? 3 : 0;
+    for (int q = 0; q < 3; ++q) { p.F[q] = c->F[fo + q]; p.G[q] = c->F[go + q]; p.box[q] = c->ubox[go + q]; }
+    p.C = c->C[half];
+    if (!p.C) { set_error("init_update_constants() has not been called (no coefficients uploaded)"); return 1; }
+    const bool nb = half == IES_HALF_H ? c->has_next : c->has_prev;
+    p.halo[0] = nb ? c->halo_recv[half][0] : nullptr;
+    p.halo[1] = nb ? c->halo_recv[half][1] : nullptr;
+    p.dz[0] = c->scratch[0]; p.dz[1] = c->scratch[1];
+    p.dxs[0] = c->scratch[2]; p.dxs[1] = c->scratch[3];
+    p.nx = c->cfg.nx; p.ny = c->cfg.ny; p.nz = c->cfg.nz;
+    p.dir = half == IES_HALF_H ? +1 : -1;
+    p.i0 = 0; p.i1 = c->cfg.nx;
+    p.pstd = c->cfg.method == IES_PSTD;
+    p.rdx = 1.0 / c->cfg.dx; p.rdy = 1.0 / c->cfg.dy; p.rdz = 1.0 / c->cfg.dz;
+    p.nterms = (int)c->terms[half].size();
+    for (int t = 0; t < p.nterms; ++t) p.terms[t] = c->terms[half][t];
+    return 0;
+}
+
+template <typename T, bool CP>
+static int do_update(ies_ctx* c, int half) {
+    UpdParams p;
+    if (fill_params(c, half, p)) return 1;
+    const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
+    if (c->cfg.method == IES_FDTD) {
+        // ghost copies on the differentiated field, axis order x, y, z (space.py:1798-1858)
+        for (int a = 0; a < 3; ++a) {
+            if (!c->ghost_on[a]) continue;
+            const int dims[3] = {nx, ny, nz};
+            if (dims[a] < 4) { set_error("periodic axis needs >= 4 cells"); return 1; }
+            const long per = (long)(a == 0 ? ny : nx) * (a == 2 ? ny : nz);
+            const long tot = per * 3 + 2L * (ny > nz ? ny : nz);
+            void* h0 = (a > 0 && p.halo[0]) ? const_cast<void*>(p.halo[0]) : nullptr;
+            void* h1 = (a > 0 && p.halo[1]) ? const_cast<void*>(p.halo[1]) : nullptr;
+            k_ghost<T, CP><<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(
+                const_cast<void*>(p.F[0]), const_cast<void*>(p.F[1]), const_cast<void*>(p.F[2]), h0, h1,
+                nx, ny, nz, a, make_double2(c->ghost_pp[a][0], c->ghost_pp[a][1]),
+                make_double2(c->ghost_pm[a][0], c->ghost_pm[a][1]));
+            count_launch();
+        }
+        dim3 blk(nz >= 64 ? 64 : 32, nz >= 64 ? 4 : 8, 1);
+        dim3 grid((nz + blk.x - 1) / blk.x, (ny + blk.y - 1) / blk.y, nx);
+        k_fdtd<T, CP><<<grid, blk, 0, c->stream>>>(p);
+        count_launch();
+        IES_CUDA(cudaGetLastError());
+        return 0;
+    }
+    for (int a = 1; a < 3; ++a)
+        if (!c->mult[half][a]) { set_error("spectral multiplier not set (malloc()/init_update_constants() missing)"); return 1; }
+    if (c->cfg.method == IES_PSTD) {
+        if (!c->mult[half][0]) { set_error("x multiplier not set"); return 1; }
+        if (launch_xline<T, CP>(c, p.F[2], p.F[1], c->scratch[2], c->scratch[3], half)) return 1;
+    }
+    if (launch_zline<T, CP>(c, p.F[1], p.F[0], c->scratch[0], c->scratch[1], half, 0, nx)) return 1;
+    if (launch_yline_update<T, CP>(c, p, half)) return 1;
+    return 0;
+}
+
+extern "C" {
+
+const char* ies_last_error(void) { return g_err.c_str(); }
+int64_t ies_launch_count(void) { return g_launches.load(); }
+
+int ies_device_count(int* n) { IES_CUDA(cudaGetDeviceCount(n)); return 0; }
+
+int ies_create(const ies_config* cfg, ies_ctx** out) {
+    if (!cfg || !out) { set_error("null argument"); return 1; }
+    if (cfg->nx < 1 || cfg->ny < 2 || cfg->nz < 2) { set_error("bad grid"); return 1; }
+    if (cfg->dtype < 0 || cfg->dtype > 3 || cfg->method < 0 || cfg->method > 2) { set_error("bad dtype/method"); return 1; }
+    if (cfg->method != IES_FDTD) {
+        if (!fft_len_supported(cfg->ny) || !fft_len_supported(cfg->nz) ||
+            (cfg->method == IES_PSTD && !fft_len_supported(cfg->nx))) {
+            set_error("SHPF/PSTD need power-of-two FFT axes in 16..512 (got ny=" + std::to_string(cfg->ny) +
+                      ", nz=" + std::to_string(cfg->nz) + (cfg->method == IES_PSTD ? ", nx=" + std::to_string(cfg->nx) : "") + ")");
+            return 1;
+        }
+    }
+    int ndev = 0;
+    IES_CUDA(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) { set_error("no such CUDA device"); return 1; }
+    IES_CUDA(cudaSetDevice(cfg->device));
+    ies_ctx* c = new ies_ctx();
+    c->cfg = *cfg;
+    c->cplx = cfg->dtype >= 2;
+    c->dbl = (cfg->dtype & 1) != 0;
+    c->esize = (c->dbl ? 8 : 4) * (c->cplx ? 2 : 1);
+    IES_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    IES_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    const size_t ncell = (size_t)cfg->nx * cfg->ny * cfg->nz;
+    const size_t fbytes = ncell * c->esize;
+    for (int q = 0; q < 6; ++q) if (dev_alloc(c, &c->F[q], fbytes)) return 1;
+    for (int h = 0; h < 2; ++h) { c->C[h] = nullptr; }
+    for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
+    if (cfg->method != IES_FDTD) {
+        if (dev_alloc(c, &c->scratch[0], fbytes) || dev_alloc(c, &c->scratch[1], fbytes)) return 1;
+        if (cfg->method == IES_PSTD)
+            if (dev_alloc(c, &c->scratch[2], fbytes) || dev_alloc(c, &c->scratch[3], fbytes)) return 1;
+    }
+    const size_t pbytes = (size_t)cfg->ny * cfg->nz * c->esize;
+    for (int h = 0; h < 2; ++h) for (int w = 0; w < 2; ++w) if (dev_alloc(c, &c->halo_recv[h][w], pbytes)) return 1;
+    for (int h = 0; h < 2; ++h) for (int a = 0; a < 3; ++a) c->mult[h][a] = nullptr;
+    // master twiddles W_N[k] = exp(-2 pi i k / N) per axis, in FFT precision
+    const int dims[3] = {cfg->nx, cfg->ny, cfg->nz};
+    for (int a = 0; a < 3; ++a) {
+        c->tw[a] = nullptr;
+        if (cfg->method == IES_FDTD || (a == 0 && cfg->method != IES_PSTD)) continue;
+        const int n = dims[a];
+        std::vector<double> hd(2 * n);
+        std::vector<float> hf(2 * n);
+        for (int k = 0; k < n; ++k) {
+            const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)k / (long double)n;
+            hd[2 * k] = (double)cosl(ang); hd[2 * k + 1] = (double)sinl(ang);
+            hf[2 * k] = (float)hd[2 * k]; hf[2 * k + 1] = (float)hd[2 * k + 1];
+        }
+        const size_t b = (size_t)2 * n * (c->dbl ? 8 : 4);
+        if (dev_alloc(c, &c->tw[a], b, false)) return 1;
+        IES_CUDA(cudaMemcpyAsync(c->tw[a], c->dbl ? (void*)hd.data() : (void*)hf.data(), b, cudaMemcpyHostToDevice, c->stream));
+        IES_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    for (int q = 0; q < 6; ++q) {
+        c->ubox[q].lo[0] = c->ubox[q].lo[1] = c->ubox[q].lo[2] = 0;
+        c->ubox[q].hi[0] = cfg->nx; c->ubox[q].hi[1] = cfg->ny; c->ubox[q].hi[2] = cfg->nz;
+    }
+    for (int a = 0; a < 3; ++a) c->ghost_on[a] = 0;
+    c->has_prev = cfg->rank > 0;
+    c->has_next = cfg->rank < cfg->nranks - 1;
+    c->stage = nullptr; c->stage_bytes = 0;
+    IES_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return 0;
+}
+
+int ies_destroy(ies_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->cfg.device);
+    cudaStreamSynchronize(c->stream);
+    for (void* p : c->owned) cudaFree(p);
+    if (c->stage) cudaFree(c->stage);
+    cudaEventDestroy(c->ev_halo);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return 0;
+}
+
+int ies_set_stream(ies_ctx* c, void* s) { c->stream = s ? (cudaStream_t)s : c->own_stream; return 0; }
+int ies_sync(ies_ctx* c) { IES_CUDA(cudaSetDevice(c->cfg.device)); IES_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
+
+int ies_set_coeff(ies_ctx* c, int half, const double* host, int64_t n) {
+    const size_t ncell = (size_t)c->cfg.nx * c->cfg.ny * c->cfg.nz;
+    if (half < 0 || half > 1 || (size_t)n != ncell) { set_error("ies_set_coeff: bad size"); return 1; }
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    if (!c->C[half]) { void* p; if (dev_alloc(c, &p, ncell * 8, false)) return 1; c->C[half] = (double*)p; }
+    IES_CUDA(cudaMemcpyAsync(c->C[half], host, ncell * 8, cudaMemcpyHostToDevice, c->stream));
+    IES_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ies_set_update_box(ies_ctx* c, int comp, const int32_t lo[3], const int32_t hi[3]) {
+    if (comp < 0 || comp > 5) { set_error("bad component"); return 1; }
+    for (int a = 0; a < 3; ++a) { c->ubox[comp].lo[a] = lo[a]; c->ubox[comp].hi[a] = hi[a]; }
+    return 0;
+}
+
+int ies_set_multiplier(ies_ctx* c, int half, int axis, const double* re_im, int32_t n) {
+    const int dims[3] = {c->cfg.nx, c->cfg.ny, c->cfg.nz};
+    if (half < 0 || half > 1 || axis < 0 || axis > 2 || n != dims[axis]) { set_error("ies_set_multiplier: bad args"); return 1; }
+    if (!fft_len_supported(n)) { set_error("ies_set_multiplier: unsupported length"); return 1; }
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    const size_t b = (size_t)2 * n * (c->dbl ? 8 : 4);
+    if (!c->mult[half][axis]) if (dev_alloc(c, &c->mult[half][axis], b, false)) return 1;
+    // fold the 1/N of the inverse transform into the table (exact: N is a power of two)
+    std::vector<double> hd(2 * n);
+    std::vector<float> hf(2 * n);
+    for (int k = 0; k < 2 * n; ++k) { hd[k] = re_im[k] / (double)n; hf[k] = (float)hd[k]; }
+    IES_CUDA(cudaMemcpyAsync(c->mult[half][axis], c->dbl ? (void*)hd.data() : (void*)hf.data(), b, cudaMemcpyHostToDevice, c->stream));
+    IES_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ies_clear_pml(ies_ctx* c) { c->terms[0].clear(); c->terms[1].clear(); return 0; }
+
+int ies_add_pml_term(ies_ctx* c, const ies_pml_term* t) {
+    if (!t || t->half < 0 || t->half > 1 || t->comp < 0 || t->comp > 2 || t->diff < 0 || t->diff > 5 || t->axis < 0 || t->axis > 2) {
+        set_error("ies_add_pml_term: bad term"); return 1;
+    }
+    if ((int)c->terms[t->half].size() >= MAX_TERMS) { set_error("too many CPML terms"); return 1; }
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    PmlTermDev d;
+    d.comp = t->comp; d.diff = t->diff; d.axis = t->axis; d.psi_off = t->psi_off; d.sign = t->sign;
+    const int dims[3] = {c->cfg.nx, c->cfg.ny, c->cfg.nz};
+    for (int a = 0; a < 3; ++a) {
+        d.lo[a] = t->lo[a]; d.hi[a] = t->hi[a];
+        if (t->lo[a] < 0 || t->hi[a] > dims[a]) { set_error("CPML box out of range"); return 1; }
+        d.pdim[a] = (a == t->axis) ? t->psi_thick : dims[a];
+    }
+    const int len = t->hi[t->axis] - t->lo[t->axis];
+    if (len < 0 || len + t->psi_off > t->psi_thick) { set_error("CPML psi range"); return 1; }
+    const size_t pb = (size_t)d.pdim[0] * d.pdim[1] * d.pdim[2] * c->esize;
+    if (dev_alloc(c, &d.psi, pb)) return 1;
+    void* tb;
+    const int L = len > 0 ? len : 1;
+    if (dev_alloc(c, &tb, (size_t)3 * L * 8, false)) return 1;
+    double* tbd = (double*)tb;
+    if (len > 0) {
+        IES_CUDA(cudaMemcpyAsync(tbd, t->b, (size_t)len * 8, cudaMemcpyHostToDevice, c->stream));
+        IES_CUDA(cudaMemcpyAsync(tbd + L, t->a, (size_t)len * 8, cudaMemcpyHostToDevice, c->stream));
+        IES_CUDA(cudaMemcpyAsync(tbd + 2 * L, t->kf, (size_t)len * 8, cudaMemcpyHostToDevice, c->stream));
+        IES_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    d.b = tbd; d.a = tbd + L; d.kf = tbd + 2 * L;
+    c->terms[t->half].push_back(d);
+    return 0;
+}
+
+int ies_set_ghost(ies_ctx* c, int axis, int enabled, double ppr, double ppi, double pmr, double pmi) {
+    if (axis < 0 || axis > 2) { set_error("bad axis"); return 1; }
+    c->ghost_on[axis] = enabled;
+    c->ghost_pp[axis][0] = ppr; c->ghost_pp[axis][1] = ppi;
+    c->ghost_pm[axis][0] = pmr; c->ghost_pm[axis][1] = pmi;
+    return 0;
+}
+
+int ies_set_neighbours(ies_ctx* c, int has_prev, int has_next) { c->has_prev = has_prev; c->has_next = has_next; return 0; }
+
+int ies_update_h(ies_ctx* c, int64_t) {
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    DISPATCH(c, return (do_update<T, CP>(c, IES_HALF_H)));
+    return 0;
+}
+int ies_update_e(ies_ctx* c, int64_t) {
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    DISPATCH(c, return (do_update<T, CP>(c, IES_HALF_E)));
+    return 0;
+}
+
+int ies_halo_send_ptr(ies_ctx* c, int half, int which, void** dev, int64_t* bytes) {
+    const size_t pb = (size_t)c->cfg.ny * c->cfg.nz * c->esize;
+    if (half == IES_HALF_H) *dev = c->F[which ? IES_EZ : IES_EY];                                   // plane 0
+    else *dev = (char*)c->F[which ? IES_HZ : IES_HY] + (size_t)(c->cfg.nx - 1) * pb;                // plane -1
+    *bytes = (int64_t)pb;
+    return 0;
+}
+int ies_halo_recv_ptr(ies_ctx* c, int half, int which, void** dev, int64_t* bytes) {
+    *dev = c->halo_recv[half][which];
+    *bytes = (int64_t)c->cfg.ny * c->cfg.nz * c->esize;
+    return 0;
+}
+int ies_halo_copy(ies_ctx* dst, ies_ctx* src, int half) {
+    // order after everything queued on src's stream, run the copies on dst's stream
+    IES_CUDA(cudaSetDevice(src->cfg.device));
+    IES_CUDA(cudaEventRecord(src->ev_halo, src->stream));
+    IES_CUDA(cudaSetDevice(dst->cfg.device));
+    IES_CUDA(cudaStreamWaitEvent(dst->stream, src->ev_halo, 0));
+    for (int w = 0; w < 2; ++w) {
+        void* s; int64_t b;
+        ies_halo_send_ptr(src, half, w, &s, &b);
+        IES_CUDA(cudaMemcpyPeerAsync(dst->halo_recv[half][w], dst->cfg.device, s, src->cfg.device, (size_t)b, dst->stream));
+    }
+    // src must not overwrite the sent planes before the copy ran
+    IES_CUDA(cudaEventRecord(dst->ev_halo, dst->stream));
+    IES_CUDA(cudaSetDevice(src->cfg.device));
+    IES_CUDA(cudaStreamWaitEvent(src->stream, dst->ev_halo, 0));
+    return 0;
+}
+
+static int check_box(ies_ctx* c, const int32_t lo[3], const int32_t hi[3], Box& bx) {
+    const int dims[3] = {c->cfg.nx, c->cfg.ny, c->cfg.nz};
+    for (int a = 0; a < 3; ++a) {
+        if (lo[a] < 0 || hi[a] > dims[a] || hi[a] < lo[a]) { set_error("box out of range"); return 1; }
+        bx.lo[a] = lo[a]; bx.hi[a] = hi[a];
+    }
+    return 0;
+}
+
+int ies_put_src(ies_ctx* c, int comp, const int32_t lo[3], const int32_t hi[3], double re, double im, int hard,
+                const double* px, const double* py, const double* pz) {
+    if (comp < 0 || comp > 5) { set_error("bad component"); return 1; }
+    Box bx; if (check_box(c, lo, hi, bx)) return 1;
+    const long n = (long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    if (n <= 0) return 0;
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    double2 *dpx = nullptr, *dpy = nullptr, *dpz = nullptr;
+    void* tmp = nullptr;
+    if (px && py && pz) {
+        if (!c->cplx) { set_error("Bloch phase tables need a complex field dtype"); return 1; }
+        const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
+        IES_CUDA(cudaMallocAsync(&tmp, (size_t)(ex + ey + ez) * 16, c->stream));
+        dpx = (double2*)tmp; dpy = dpx + ex; dpz = dpy + ey;
+        IES_CUDA(cudaMemcpyAsync(dpx, px, (size_t)ex * 16, cudaMemcpyHostToDevice, c->stream));
+        IES_CUDA(cudaMemcpyAsync(dpy, py, (size_t)ey * 16, cudaMemcpyHostToDevice, c->stream));
+        IES_CUDA(cudaMemcpyAsync(dpz, pz, (size_t)ez * 16, cudaMemcpyHostToDevice, c->stream));
+    }
+    DISPATCH(c, k_put_src<T, CP><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
+        c->F[comp], c->cfg.ny, c->cfg.nz, bx, make_double2(re, im), hard, dpx, dpy, dpz));
+    count_launch();
+    IES_CUDA(cudaGetLastError());
+    if (tmp) IES_CUDA(cudaFreeAsync(tmp, c->stream));
+    return 0;
+}
+
+static int ensure_stage(ies_ctx* c, size_t bytes) {
+    if (c->stage_bytes >= bytes) return 0;
+    if (c->stage) cudaFree(c->stage);
+    c->stage = nullptr; c->stage_bytes = 0;
+    IES_CUDA(cudaMalloc(&c->stage, bytes));
+    c->stage_bytes = bytes;
+    return 0;
+}
+
+static int pack_launch(ies_ctx* c, void* f, Box bx, long n, int unpack) {
+    const unsigned grid = (unsigned)std::min<long>((n + 255) / 256, 148L * 16);
+    switch (c->esize) {
+        case 4:  k_pack<float><<<grid, 256, 0, c->stream>>>((const float*)f, (float*)c->stage, c->cfg.ny, c->cfg.nz, bx, unpack); break;
+        case 8:  k_pack<double><<<grid, 256, 0, c->stream>>>((const double*)f, (double*)c->stage, c->cfg.ny, c->cfg.nz, bx, unpack); break;
+        default: k_pack<double2><<<grid, 256, 0, c->stream>>>((const double2*)f, (double2*)c->stage, c->cfg.ny, c->cfg.nz, bx, unpack); break;
+    }
+    count_launch();
+    IES_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ies_get_field(ies_ctx* c, int comp, const int32_t lo[3], const int32_t hi[3], void* host) {
+    if (comp < 0 || comp > 5) { set_error("bad component"); return 1; }
+    Box bx; if (check_box(c, lo, hi, bx)) return 1;
+    const long n = (long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    if (n <= 0) return 0;
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    const bool whole_planes = lo[1] == 0 && lo[2] == 0 && hi[1] == c->cfg.ny && hi[2] == c->cfg.nz;
+    if (whole_planes) {
+        const size_t pb = (size_t)c->cfg.ny * c->cfg.nz * c->esize;
+        IES_CUDA(cudaMemcpyAsync(host, (char*)c->F[comp] + lo[0] * pb, (size_t)(hi[0] - lo[0]) * pb, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        if (ensure_stage(c, (size_t)n * c->esize)) return 1;
+        if (pack_launch(c, c->F[comp], bx, n, 0)) return 1;
+        IES_CUDA(cudaMemcpyAsync(host, c->stage, (size_t)n * c->esize, cudaMemcpyDeviceToHost, c->stream));
+    }
+    IES_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ies_set_field(ies_ctx* c, int comp, const int32_t lo[3], const int32_t hi[3], const void* host) {
+    if (comp < 0 || comp > 5) { set_error("bad component"); return 1; }
+    Box bx; if (check_box(c, lo, hi, bx)) return 1;
+    const long n = (long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    if (n <= 0) return 0;
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    const bool whole_planes = lo[1] == 0 && lo[2] == 0 && hi[1] == c->cfg.ny && hi[2] == c->cfg.nz;
+    if (whole_planes) {
+        const size_t pb = (size_t)c->cfg.ny * c->cfg.nz * c->esize;
+        IES_CUDA(cudaMemcpyAsync((char*)c->F[comp] + lo[0] * pb, host, (size_t)(hi[0] - lo[0]) * pb, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        if (ensure_stage(c, (size_t)n * c->esize)) return 1;
+        IES_CUDA(cudaMemcpyAsync(c->stage, host, (size_t)n * c->esize, cudaMemcpyHostToDevice, c->stream));
+        if (pack_launch(c, c->F[comp], bx, n, 1)) return 1;
+    }
+    IES_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int ies_field_ptr(ies_ctx* c, int comp, void** dev) {
+    if (comp < 0 || comp > 5) { set_error("bad component"); return 1; }
+    *dev = c->F[comp];
+    return 0;
+}
+
+// ---------------------------------------------------------------- collectors
+int ies_dft_create(ies_ctx* c, const int32_t lo[3], const int32_t hi[3], const int32_t comps[4],
+                   const double* freqs, int32_t nf, ies_dft** out) {
+    Box bx; if (check_box(c, lo, hi, bx)) return 1;
+    if (nf < 1) { set_error("nf < 1"); return 1; }
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    ies_dft* d = new ies_dft();
+    d->ctx = c; d->box = bx; d->nf = nf;
+    d->ncell = (long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
+    for (int q = 0; q < 4; ++q) {
+        if (comps[q] < 0 || comps[q] > 5) { set_error("bad component"); delete d; return 1; }
+        d->comps[q] = comps[q];
+        const size_t b = (size_t)nf * (d->ncell > 0 ? d->ncell : 1) * 16;
+        IES_CUDA(cudaMalloc((void**)&d->acc[q], b));
+        IES_CUDA(cudaMemsetAsync(d->acc[q], 0, b, c->stream));
+    }
+    IES_CUDA(cudaMalloc((void**)&d->freqs, (size_t)nf * 8));
+    IES_CUDA(cudaMalloc((void**)&d->phase, (size_t)nf * 16));
+    IES_CUDA(cudaMemcpyAsync(d->freqs, freqs, (size_t)nf * 8, cudaMemcpyHostToDevice, c->stream));
+    IES_CUDA(cudaStreamSynchronize(c->stream));
+    *out = d;
+    return 0;
+}
+
+int ies_dft_accumulate(ies_dft* d, ies_ctx* a, ies_ctx* b, int64_t tstep) {
+    if (d->ncell <= 0) return 0;
+    if (a->cfg.device != d->ctx->cfg.device || (b && b->cfg.device != a->cfg.device)) { set_error("collector spaces must share a device"); return 1; }
+    if (b && (b->cfg.dtype != a->cfg.dtype || b->cfg.nx != a->cfg.nx || b->cfg.ny != a->cfg.ny || b->cfg.nz != a->cfg.nz)) {
+        set_error("get_SF: TF and IF differ in shape/dtype"); return 1;
+    }
+    IES_CUDA(cudaSetDevice(a->cfg.device));
+    cudaStream_t st = a->stream;
+    if (b && b->stream != a->stream) {
+        IES_CUDA(cudaEventRecord(b->ev_halo, b->stream));
+        IES_CUDA(cudaStreamWaitEvent(st, b->ev_halo, 0));
+    }
+    k_dft_phase<<<(d->nf + 127) / 128, 128, 0, st>>>(d->freqs, d->nf, (double)tstep, a->cfg.dt, d->phase);
+    DftDev dd; dd.nf = d->nf; dd.ncell = d->ncell;
+    for (int q = 0; q < 4; ++q) dd.acc[q] = d->acc[q];
+    const void* fa[4]; const void* fb[4];
+    for (int q = 0; q < 4; ++q) { fa[q] = a->F[d->comps[q]]; fb[q] = b ? b->F[d->comps[q]] : nullptr; }
+    DISPATCH(a, k_dft_acc<T, CP><<<(unsigned)((d->ncell + 255) / 256), 256, 0, st>>>(
+        dd, fa[0], fa[1], fa[2], fa[3], fb[0], fb[1], fb[2], fb[3], a->cfg.ny, a->cfg.nz, d->box, d->phase, a->cfg.dt));
+    count_launch(2);
+    IES_CUDA(cudaGetLastError());
+    if (b && b->stream != a->stream) {
+        IES_CUDA(cudaEventRecord(a->ev_halo, st));
+        IES_CUDA(cudaStreamWaitEvent(b->stream, a->ev_halo, 0));
+    }
+    return 0;
+}
+
+int ies_dft_read(ies_dft* d, int which, void* host) {
+    if (which < 0 || which > 3) { set_error("bad index"); return 1; }
+    IES_CUDA(cudaSetDevice(d->ctx->cfg.device));
+    IES_CUDA(cudaStreamSynchronize(d->ctx->stream));
+    IES_CUDA(cudaDeviceSynchronize());
+    IES_CUDA(cudaMemcpy(host, d->acc[which], (size_t)d->nf * d->ncell * 16, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ies_dft_destroy(ies_dft* d) {
+    if (!d) return 0;
+    cudaSetDevice(d->ctx->cfg.device);
+    cudaDeviceSynchronize();
+    for (int q = 0; q < 4; ++q) cudaFree(d->acc[q]);
+    cudaFree(d->freqs); cudaFree(d->phase);
+    delete d;
+    return 0;
+}
+
+int ies_probe_create(ies_ctx* c, int32_t i, int32_t j, int32_t k, int64_t tsteps, ies_probe** out) {
+    if (i < 0 || i >= c->cfg.nx || j < 0 || j >= c->cfg.ny || k < 0 || k >= c->cfg.nz || tsteps < 1) { set_error("probe out of range"); return 1; }
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    ies_probe* p = new ies_probe();
+    p->ctx = c; p->tsteps = (long)tsteps;
+    p->idx = ((size_t)i * c->cfg.ny + j) * c->cfg.nz + k;
+    IES_CUDA(cudaMalloc(&p->buf, (size_t)6 * tsteps * c->esize));
+    IES_CUDA(cudaMemset(p->buf, 0, (size_t)6 * tsteps * c->esize));
+    *out = p;
+    return 0;
+}
+
+int ies_probe_record(ies_probe* p, ies_ctx* a, ies_ctx* b, int64_t tstep) {
+    if (tstep < 0 || tstep >= p->tsteps) { set_error("probe: tstep out of range"); return 1; }
+    IES_CUDA(cudaSetDevice(a->cfg.device));
+    if (b && b->stream != a->stream) {
+        IES_CUDA(cudaEventRecord(b->ev_halo, b->stream));
+        IES_CUDA(cudaStreamWaitEvent(a->stream, b->ev_halo, 0));
+    }
+    const void* fb[6];
+    for (int q = 0; q < 6; ++q) fb[q] = b ? b->F[q] : nullptr;
+    DISPATCH(a, k_probe<T, CP><<<1, 32, 0, a->stream>>>(p->buf, p->tsteps, (long)tstep, a->F[0], a->F[1], a->F[2],
+        a->F[3], a->F[4], a->F[5], fb[0], fb[1], fb[2], fb[3], fb[4], fb[5], p->idx));
+    count_launch();
+    IES_CUDA(cudaGetLastError());
+    if (b && b->stream != a->stream) {
+        IES_CUDA(cudaEventRecord(a->ev_halo, a->stream));
+        IES_CUDA(cudaStreamWaitEvent(b->stream, a->ev_halo, 0));
+    }
+    return 0;
+}
+
+int ies_probe_read(ies_probe* p, int comp, void* host) {
+    if (comp < 0 || comp > 5) { set_error("bad component"); return 1; }
+    IES_CUDA(cudaSetDevice(p->ctx->cfg.device));
+    IES_CUDA(cudaDeviceSynchronize());
+    const size_t b = (size_t)p->tsteps * p->ctx->esize;
+    IES_CUDA(cudaMemcpy(host, (char*)p->buf + comp * b, b, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ies_probe_destroy(ies_probe* p) {
+    if (!p) return 0;
+    cudaSetDevice(p->ctx->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(p->buf);
+    delete p;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,81 @@
+// Internal declarations shared by the translation units of libies_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ies_b200.h"
+
+namespace ies {
+
+constexpr int MAX_TERMS = 12;   // 6 faces x 2 components per half-step (space.py:1054-1108)
+
+struct Box { int lo[3], hi[3]; };
+
+struct PmlTermDev {
+    int comp, diff, axis;
+    int lo[3], hi[3];
+    int psi_off;
+    int pdim[3];                // psi array extents
+    double sign;
+    void* psi;                  // field dtype
+    const double *b, *a, *kf;   // per-cell-along-axis tables (device)
+};
+
+// Everything one half-step update kernel needs, passed by value.
+struct UpdParams {
+    const void* F[3];           // differentiated field (E in updateH, H in updateE): x,y,z
+    void* G[3];                 // updated field
+    const double* C;            // CH2 / CE2 (space.py:445-553, zero conductivity)
+    const void* halo[2];        // neighbour planes of F_y, F_z (or null)
+    const void* dz[2];          // scratch: d/dz F_y, d/dz F_x   (spectral methods)
+    const void* dxs[2];         // scratch: d/dx F_z, d/dx F_y   (PSTD)
+    int nx, ny, nz;
+    int dir;                    // +1: forward differences (updateH); -1: backward (updateE)
+    int i0, i1;                 // x range handled by this launch
+    int pstd;                   // x derivative comes from dxs[]
+    double rdx, rdy, rdz;
+    Box box[3];
+    int nterms;
+    PmlTermDev terms[MAX_TERMS];
+};
+
+struct Ctx {
+    ies_config cfg;
+    int esize;                  // bytes per field element
+    bool cplx, dbl;
+    cudaStream_t stream, own_stream;
+    void* F[6];
+    double* C[2];
+    void* scratch[4];           // dzA dzB dxA dxB
+    void* halo_recv[2][2];
+    void* mult[2][3];           // [half][axis] complex table in FFT precision, pre-scaled by 1/N
+    void* tw[3];                // W_N master twiddles per axis
+    Box ubox[6];
+    std::vector<PmlTermDev> terms[2];
+    std::vector<void*> owned;   // device allocations freed at destroy
+    int ghost_on[3];
+    double ghost_pp[3][2], ghost_pm[3][2];
+    int has_prev, has_next;
+    void* stage; size_t stage_bytes;   // staging buffer for get/set
+    cudaEvent_t ev_halo;
+};
+
+void set_error(const std::string& s);
+void count_launch(int n = 1);
+#define IES_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    ies::set_error(std::string(#x) + ": " + cudaGetErrorString(e_)); return 1; } } while (0)
+
+// spectral_*.cu: z-line / strided-line derivative passes and the fused y-line update.
+// All return 0 or set the error and return 1.
+template <typename T, bool CPLX>
+int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int i0, int i1);
+template <typename T, bool CPLX>
+int launch_xline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half);
+template <typename T, bool CPLX>
+int launch_yline_update(Ctx* c, const UpdParams& p, int half);
+
+bool fft_len_supported(int n);
+
+}  // namespace ies

@@ -1,0 +1,196 @@
+// Register/shared-memory Stockham FFT building block for the spectral derivatives
+// (replaces xp.fft.{r,}fftn / i{r,}fftn of space.py:145-162, call sites 709-755, 903-961).
+//
+// One FFT line of length N (power of two, 16..1024) is handled by T = N/16 threads,
+// each holding 16 complex values in registers.  Stages are radix 16/16/(N/256);
+// values cross threads through a shared-memory exchange buffer whose addressing is
+// supplied by the caller (contiguous-line or strided-line policy).  The forward
+// transform ends, and the inverse begins, with the same register<->index map, so the
+// spectral multiplier ik*exp(+-ik d/2) is applied in registers with no exchange.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ies {
+
+template <typename T> struct Cx;
+template <> struct Cx<float>  { using type = float2; };
+template <> struct Cx<double> { using type = double2; };
+
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+    C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+template <typename C> __device__ __forceinline__ C cmulc(C a, C b) {   // a * conj(b)
+    C r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r;
+}
+
+// cos/sin(2*pi*k/16), k = 0..7
+__device__ __forceinline__ constexpr double tw16_cos(int k) {
+    return k == 0 ? 1.0 : k == 1 ? 0.92387953251128673848 : k == 2 ? 0.70710678118654752440
+         : k == 3 ? 0.38268343236508977173 : k == 4 ? 0.0 : k == 5 ? -0.38268343236508977173
+         : k == 6 ? -0.70710678118654752440 : -0.92387953251128673848;
+}
+__device__ __forceinline__ constexpr double tw16_sin(int k) {
+    return k == 0 ? 0.0 : k == 1 ? 0.38268343236508977173 : k == 2 ? 0.70710678118654752440
+         : k == 3 ? 0.92387953251128673848 : k == 4 ? 1.0 : k == 5 ? 0.92387953251128673848
+         : k == 6 ? 0.70710678118654752440 : 0.38268343236508977173;
+}
+
+// In-register R-point DFT, decimation in time, natural order in and out.
+// INV=false: exp(-2 pi i nk/R); INV=true: exp(+2 pi i nk/R), unnormalised.
+template <int R, bool INV, typename C> struct Dft;
+
+template <bool INV, typename C> struct Dft<1, INV, C> {
+    static __device__ __forceinline__ void run(const C (&in)[1], C (&out)[1]) { out[0] = in[0]; }
+};
+template <bool INV, typename C> struct Dft<2, INV, C> {
+    static __device__ __forceinline__ void run(const C (&in)[2], C (&out)[2]) {
+        out[0] = cadd(in[0], in[1]);
+        out[1] = csub(in[0], in[1]);
+    }
+};
+template <int R, bool INV, typename C> struct Dft {
+    static __device__ __forceinline__ void run(const C (&in)[R], C (&out)[R]) {
+        C e[R / 2], o[R / 2], E[R / 2], O[R / 2];
+#pragma unroll
+        for (int i = 0; i < R / 2; ++i) { e[i] = in[2 * i]; o[i] = in[2 * i + 1]; }
+        Dft<R / 2, INV, C>::run(e, E);
+        Dft<R / 2, INV, C>::run(o, O);
+#pragma unroll
+        for (int k = 0; k < R / 2; ++k) {
+            C t;
+            constexpr int S = 16 / R;                  // index step into the 16th-root table
+            if (k == 0) {
+                t = O[k];
+            } else if (4 * k == R) {                   // -i (forward) / +i (inverse)
+                if (INV) { t.x = -O[k].y; t.y = O[k].x; } else { t.x = O[k].y; t.y = -O[k].x; }
+            } else {
+                using Tr = decltype(t.x);
+                const Tr c = (Tr)tw16_cos(k * S), s = (Tr)tw16_sin(k * S);
+                if (INV) { t.x = O[k].x * c - O[k].y * s; t.y = O[k].x * s + O[k].y * c; }
+                else     { t.x = O[k].x * c + O[k].y * s; t.y = O[k].y * c - O[k].x * s; }
+            }
+            out[k]         = cadd(E[k], t);
+            out[k + R / 2] = csub(E[k], t);
+        }
+    }
+};
+
+template <int N> struct Plan {
+    static_assert(N >= 16 && N <= 1024 && (N & (N - 1)) == 0, "FFT length must be 16..1024, power of two");
+    static constexpr int T  = N / 16;                        // threads per line
+    static constexpr int R1 = (N / 16 >= 16) ? 16 : N / 16;  // second radix (1 if N == 16)
+    static constexpr int R2 = N / (16 * R1);                 // third radix (1, 2 or 4)
+    static constexpr int RL = (R2 > 1) ? R2 : (R1 > 1 ? R1 : 16);   // radix adjacent to the spectrum
+};
+
+// One Stockham stage on the 16 register values of a thread.
+//   v[b*R + m] <-> input element  j + m*N/R,  j = t + T*b   (b < 16/R butterflies per thread)
+// LOAD : read inputs from the exchange buffer;  STORE: write outputs to it at
+//   (j/NS)*NS*R + (j%NS) + m*NS.   Without STORE the outputs stay in v[b*R+m].
+// tw: master twiddle table W_N[k] = exp(-2 pi i k/N) (shared memory).
+template <int N, int R, int NS, bool INV, bool LOAD, bool STORE, typename C, typename X>
+__device__ __forceinline__ void fft_stage(C (&v)[16], const int t, const C* __restrict__ tw, X& xb) {
+    constexpr int T = N / 16;
+    constexpr int NB = 16 / R;
+    if (LOAD) {
+        xb.sync();
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int j = t + T * b;
+#pragma unroll
+            for (int m = 0; m < R; ++m) v[b * R + m] = xb.ld(j + m * (N / R));
+        }
+    }
+    if (STORE) xb.sync();
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const int j = t + T * b;
+        C in[R], out[R];
+#pragma unroll
+        for (int m = 0; m < R; ++m) in[m] = v[b * R + m];
+        if (NS > 1) {
+            const int jj = j & (NS - 1);
+            constexpr int step = N / (NS * R);
+#pragma unroll
+            for (int m = 1; m < R; ++m) {
+                const C w = tw[(jj * m * step) & (N - 1)];
+                in[m] = INV ? cmulc(in[m], w) : cmul(in[m], w);
+            }
+        }
+        Dft<R, INV, C>::run(in, out);
+        if (STORE) {
+            const int base = (j / NS) * NS * R + (j & (NS - 1));
+#pragma unroll
+            for (int m = 0; m < R; ++m) xb.st(base + m * NS, out[m]);
+        } else {
+#pragma unroll
+            for (int m = 0; m < R; ++m) v[b * R + m] = out[m];
+        }
+    }
+}
+
+// Spectrum index held in v[q] after fft_forward (and expected by fft_inverse).
+template <int N> __device__ __forceinline__ int spec_index(int t, int q) {
+    constexpr int RL = Plan<N>::RL;
+    constexpr int T = N / 16;
+    const int b = q / RL, m = q % RL;
+    return t + T * b + m * (N / RL);
+}
+// Line index held in v[q] before fft_forward and after fft_inverse.
+template <int N> __device__ __forceinline__ int line_index(int t, int q) { return t + q * (N / 16); }
+
+template <int N, typename C, typename X>
+__device__ __forceinline__ void fft_forward(C (&v)[16], int t, const C* tw, X& xb) {
+    using P = Plan<N>;
+    if (N == 16) {
+        fft_stage<N, 16, 1, false, false, false>(v, t, tw, xb);
+    } else {
+        fft_stage<N, 16, 1, false, false, true>(v, t, tw, xb);
+        if (P::R2 == 1) {
+            fft_stage<N, P::R1, 16, false, true, false>(v, t, tw, xb);
+        } else {
+            fft_stage<N, P::R1, 16, false, true, true>(v, t, tw, xb);
+            fft_stage<N, (P::R2 > 1 ? P::R2 : 2), 16 * P::R1, false, true, false>(v, t, tw, xb);
+        }
+    }
+}
+
+template <int N, typename C, typename X>
+__device__ __forceinline__ void fft_inverse(C (&v)[16], int t, const C* tw, X& xb) {
+    using P = Plan<N>;
+    if (N == 16) {
+        fft_stage<N, 16, 1, true, false, false>(v, t, tw, xb);
+    } else if (P::R2 == 1) {
+        fft_stage<N, P::R1, 1, true, false, true>(v, t, tw, xb);
+        fft_stage<N, 16, P::R1, true, true, false>(v, t, tw, xb);
+    } else {
+        constexpr int R2 = (P::R2 > 1 ? P::R2 : 2);
+        fft_stage<N, R2, 1, true, false, true>(v, t, tw, xb);
+        fft_stage<N, P::R1, R2, true, true, true>(v, t, tw, xb);
+        fft_stage<N, 16, R2 * P::R1, true, true, false>(v, t, tw, xb);
+    }
+}
+
+// Exchange policies ---------------------------------------------------------------
+// Contiguous lines (z axis): threads of a line are adjacent lanes; one line per
+// T lanes; padded by one element per 16 to keep the radix-16 scatter conflict free.
+template <typename C, int N> struct XchgContig {
+    C* base;            // this line's slice of the exchange buffer
+    static constexpr int LS = N + N / 16;
+    __device__ __forceinline__ C ld(int i) const { return base[i + (i >> 4)]; }
+    __device__ __forceinline__ void st(int i, C v) const { base[i + (i >> 4)] = v; }
+    __device__ __forceinline__ void sync() const {
+        if (N / 16 <= 32) __syncwarp(); else __syncthreads();
+    }
+};
+// Strided lines (y or x axis): W adjacent lines per CTA, lane index = column.
+template <typename C, int W> struct XchgStrided {
+    C* base;            // buffer + column
+    __device__ __forceinline__ C ld(int i) const { return base[i * W]; }
+    __device__ __forceinline__ void st(int i, C v) const { base[i * W] = v; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+
+}  // namespace ies

@@ -1,0 +1,7 @@
+// Explicit instantiation of the spectral kernels for field dtype f32.
+#include "spectral.cuh"
+namespace ies {
+template int launch_zline<float, false>(Ctx*, const void*, const void*, void*, void*, int, int, int);
+template int launch_xline<float, false>(Ctx*, const void*, const void*, void*, void*, int);
+template int launch_yline_update<float, false>(Ctx*, const UpdParams&, int);
+}  // namespace ies
