@@ -82,6 +82,10 @@ SIGNATURES = {
     'ies_probe_read': (C.c_int, [_vp, C.c_int, _vp]),
     'ies_probe_destroy': (C.c_int, [_vp]),
     'ies_launch_count': (C.c_int64, []),
+    'ies_timer_start': (C.c_int, [_vp]),
+    'ies_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    'ies_profile': (C.c_int, [_vp, C.c_int]),
+    'ies_profile_read': (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 
 

@@ -16,6 +16,13 @@ static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
 void set_error(const std::string& s) { g_err = s; }
 void count_launch(int n) { g_launches += n; }
+void prof_mark(Ctx* c, int slot, int end) {
+    if (!c->profiling) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, c->stream);
+    c->prof_ev[slot][end].push_back(e);
+}
 bool fft_len_supported(int n) { return n >= 16 && n <= 512 && (n & (n - 1)) == 0; }
 
 // ------------------------------------------------------------------ FDTD -----
@@ -293,7 +300,9 @@ static int do_update(ies_ctx* c, int half) {
         }
         dim3 blk(nz >= 64 ? 64 : 32, nz >= 64 ? 4 : 8, 1);
         dim3 grid((nz + blk.x - 1) / blk.x, (ny + blk.y - 1) / blk.y, nx);
+        prof_mark(c, PROF_FDTD, 0);
         k_fdtd<T, CP><<<grid, blk, 0, c->stream>>>(p);
+        prof_mark(c, PROF_FDTD, 1);
         count_launch();
         IES_CUDA(cudaGetLastError());
         return 0;
@@ -340,6 +349,9 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     IES_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     IES_CUDA(cudaEventCreateWithFlags(&c->ev_halo, cudaEventDisableTiming));
+    IES_CUDA(cudaEventCreate(&c->ev_t0));
+    IES_CUDA(cudaEventCreate(&c->ev_t1));
+    c->profiling = 0;
     const size_t ncell = (size_t)cfg->nx * cfg->ny * cfg->nz;
     const size_t fbytes = ncell * c->esize;
     for (int q = 0; q < 6; ++q) if (dev_alloc(c, &c->F[q], fbytes)) return 1;
@@ -397,6 +409,42 @@ int ies_destroy(ies_ctx* c) {
 }
 
 int ies_set_stream(ies_ctx* c, void* s) { c->stream = s ? (cudaStream_t)s : c->own_stream; return 0; }
+int ies_timer_start(ies_ctx* c) {
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    IES_CUDA(cudaEventRecord(c->ev_t0, c->stream));
+    return 0;
+}
+int ies_timer_stop(ies_ctx* c, double* ms) {
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    IES_CUDA(cudaEventRecord(c->ev_t1, c->stream));
+    IES_CUDA(cudaEventSynchronize(c->ev_t1));
+    float f = 0.f;
+    IES_CUDA(cudaEventElapsedTime(&f, c->ev_t0, c->ev_t1));
+    *ms = (double)f;
+    return 0;
+}
+int ies_profile(ies_ctx* c, int on) {
+    for (int s = 0; s < 4; ++s) for (int e = 0; e < 2; ++e) {
+        for (cudaEvent_t ev : c->prof_ev[s][e]) cudaEventDestroy(ev);
+        c->prof_ev[s][e].clear();
+    }
+    c->profiling = on;
+    return 0;
+}
+int ies_profile_read(ies_ctx* c, int slot, double* ms_total, int64_t* launches) {
+    if (slot < 0 || slot > 3) { set_error("bad profile slot"); return 1; }
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    IES_CUDA(cudaStreamSynchronize(c->stream));
+    double tot = 0.0;
+    const size_t n = std::min(c->prof_ev[slot][0].size(), c->prof_ev[slot][1].size());
+    for (size_t i = 0; i < n; ++i) {
+        float f = 0.f;
+        IES_CUDA(cudaEventElapsedTime(&f, c->prof_ev[slot][0][i], c->prof_ev[slot][1][i]));
+        tot += f;
+    }
+    *ms_total = tot; *launches = (int64_t)n;
+    return 0;
+}
 int ies_sync(ies_ctx* c) { IES_CUDA(cudaSetDevice(c->cfg.device)); IES_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
 
 int ies_set_coeff(ies_ctx* c, int half, const double* host, int64_t n) {

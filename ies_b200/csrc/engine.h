@@ -60,7 +60,13 @@ struct Ctx {
     int has_prev, has_next;
     void* stage; size_t stage_bytes;   // staging buffer for get/set
     cudaEvent_t ev_halo;
+    cudaEvent_t ev_t0, ev_t1;          // ies_timer_start/stop
+    int profiling;                     // per-kernel CUDA-event timing on/off
+    std::vector<cudaEvent_t> prof_ev[4][2];   // [slot][begin/end]
 };
+
+enum { PROF_ZLINE = 0, PROF_YLINE_UPDATE = 1, PROF_XLINE = 2, PROF_FDTD = 3 };
+void prof_mark(Ctx* c, int slot, int end);
 
 void set_error(const std::string& s);
 void count_launch(int n = 1);

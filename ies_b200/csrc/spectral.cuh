@@ -258,7 +258,9 @@ int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
         kern<<<grid, ZCfg<NN>::THREADS, sm, c->stream>>>(A, B, dA, dB, line0, nlines,        \
             (const C*)c->tw[2], (const C*)c->mult[half][2]);                                \
     }
+    prof_mark(c, PROF_ZLINE, 0);
     IES_FOR_N(n, Z_CASE)
+    prof_mark(c, PROF_ZLINE, 1);
 #undef Z_CASE
     count_launch();
     IES_CUDA(cudaGetLastError());
@@ -279,7 +281,9 @@ int launch_xline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
         kern<<<grid, S::THREADS, sm, c->stream>>>(A, B, dA, dB, ncols, ncols,                \
             (const C*)c->tw[0], (const C*)c->mult[half][0]);                                \
     }
+    prof_mark(c, PROF_XLINE, 0);
     IES_FOR_N(n, X_CASE)
+    prof_mark(c, PROF_XLINE, 1);
 #undef X_CASE
     count_launch();
     IES_CUDA(cudaGetLastError());
@@ -300,7 +304,9 @@ int launch_yline_update(Ctx* c, const UpdParams& p, int half) {
         kern<<<grid, S::THREADS, sm, c->stream>>>(p, (const C*)c->tw[1],                     \
             (const C*)c->mult[half][1]);                                                    \
     }
+    prof_mark(c, PROF_YLINE_UPDATE, 0);
     IES_FOR_N(n, Y_CASE)
+    prof_mark(c, PROF_YLINE_UPDATE, 1);
 #undef Y_CASE
     count_launch();
     IES_CUDA(cudaGetLastError());

@@ -114,6 +114,10 @@ class DeviceField:
             return
         lo, hi, sq = b
         shp = [h - l for l, h in zip(lo, hi)]
+        if (isinstance(val, np.ndarray) and val.dtype == self.dtype and list(val.shape) == shp
+                and val.flags.c_contiguous):
+            self._set_box(lo, hi, val)      # no host staging copy
+            return
         tmp = np.empty([n for a, n in enumerate(shp) if a not in sq], dtype=self.dtype)
         tmp[...] = val          # NumPy's own casting / broadcasting rules and errors
         self._set_box(lo, hi, tmp.reshape(shp))

@@ -142,9 +142,17 @@ int ies_probe_read(ies_probe* p, int comp, void* host);
 int ies_probe_destroy(ies_probe* p);
 
 /* ---- measurement ---------------------------------------------------------- */
-/* Kernel launches issued by this library since process start (bench.py's
- * gpu_launches) and the CUDA-event time of the most recent update pair. */
+/* Kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t ies_launch_count(void);
+/* CUDA events on the context's stream: ies_timer_start ... ies_timer_stop(&ms). */
+int ies_timer_start(ies_ctx* ctx);
+int ies_timer_stop(ies_ctx* ctx, double* ms);
+/* Per-kernel CUDA-event timing.  ies_profile(ctx, 1) starts bracketing every hot-path
+ * launch with events (0 stops and clears); ies_profile_read sums the durations of slot
+ * 0 = z-line derivative, 1 = y-line derivative + fused update, 2 = x-line derivative
+ * (PSTD), 3 = FDTD update. */
+int ies_profile(ies_ctx* ctx, int on);
+int ies_profile_read(ies_ctx* ctx, int slot, double* ms_total, int64_t* launches);
 
 #ifdef __cplusplus
 }
