@@ -485,6 +485,7 @@ int ies_add_pml_term(ies_ctx* c, const ies_pml_term* t) {
     if (!t || t->half < 0 || t->half > 1 || t->comp < 0 || t->comp > 2 || t->diff < 0 || t->diff > 5 || t->axis < 0 || t->axis > 2) {
         set_error("ies_add_pml_term: bad term"); return 1;
     }
+    if (t->diff / 2 != t->comp) { set_error("ies_add_pml_term: derivative slot does not belong to the component's curl"); return 1; }
     if ((int)c->terms[t->half].size() >= MAX_TERMS) { set_error("too many CPML terms"); return 1; }
     IES_CUDA(cudaSetDevice(c->cfg.device));
     PmlTermDev d;

@@ -137,89 +137,126 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 }
 
 // ------------------------------------------ y lines + fused field update -----
-template <bool CPLX> struct Conv;
-template <> struct Conv<false> {       // real fields: one packed FFT gave both derivatives
-    template <typename C>
-    static __device__ __forceinline__ void set(double& d0, double& d5, const C (&res)[1][16], int q) {
-        d0 = (double)res[0][q].x; d5 = (double)res[0][q].y;
-    }
-};
-template <> struct Conv<true> {
-    template <typename C>
-    static __device__ __forceinline__ void set(double2& d0, double2& d5, const C (&res)[2][16], int q) {
-        d0 = make_double2((double)res[0][q].x, (double)res[0][q].y);
-        d5 = make_double2((double)res[1][q].x, (double)res[1][q].y);
-    }
-};
-
+// Phase A: W adjacent y lines (one per column, lane = column) are transformed in
+//          registers; the derivative pair lands in shared memory in tile layout
+//          stash[row * W + col].
+// Phase B: the CTA re-maps to 16-byte vectors along z (V cells per thread) and streams
+//          the cell update: PB row groups of loads are issued before any arithmetic so
+//          enough bytes are in flight to cover HBM latency.
 template <typename T, bool CPLX, int N>
-__global__ void __launch_bounds__(SCfg<T, CPLX, N>::THREADS)
+__global__ void __launch_bounds__(SCfg<T, CPLX, N>::THREADS, (SCfg<T, CPLX, N>::THREADS <= 256 ? 2 : 1))
 k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ twg,
                const typename Cx<T>::type* __restrict__ mlg) {
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
     using A = typename AccT<CPLX>::type;
-    using E = Elem<T, CPLX>;
-    constexpr int W = SCfg<T, CPLX, N>::W;
+    using VV = Vec<T, CPLX>;
+    using S = SCfg<T, CPLX, N>;
+    constexpr int W = S::W;
+    constexpr int V = VV::V;
+    constexpr int NF = F::NF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* tw = reinterpret_cast<C*>(smem_raw);
     C* ml = tw + N;
-    C* xbuf = ml + N;
+    C* xbuf = ml + N;                       // NF buffers of N*W: exchange, then derivative stash
     load_tables(tw, ml, twg, mlg, N);
-    const int c = threadIdx.x % W, t = threadIdx.x / W;
     const int k0 = blockIdx.x * W;
-    const int k = k0 + c;
     const int i = p.i0 + blockIdx.y;
-    const bool ok = k < p.nz;
     const size_t plane = (size_t)p.ny * p.nz;
-    const size_t pbase = (size_t)i * plane + k;
-    XchgStrided<C, W> xb{xbuf + c};
-    // pair (F_z, F_x): Re -> d/dy F_z (slot 0), Im -> d/dy F_x (slot 5)
-    C res[F::NF][16];
+    {
+        const int c = threadIdx.x % W, t = threadIdx.x / W;
+        const int k = k0 + c;
+        const bool ok = k < p.nz;
+        const size_t pbase = (size_t)i * plane + k;
+        // pair (F_z, F_x): Re -> d/dy F_z (slot 0), Im -> d/dy F_x (slot 5)
 #pragma unroll
-    for (int f = 0; f < F::NF; ++f) {
-        C v[16];
+        for (int f = 0; f < NF; ++f) {
+            XchgStrided<C, W> xb{xbuf + (size_t)f * N * W + c};
+            C v[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            if (ok) v[q] = F::ld(p.F[2], p.F[0], pbase + (size_t)line_index<N>(t, q) * p.nz, f);
-            else { v[q].x = 0; v[q].y = 0; }
+            for (int q = 0; q < 16; ++q) {
+                if (ok) v[q] = F::ld(p.F[2], p.F[0], pbase + (size_t)line_index<N>(t, q) * p.nz, f);
+                else { v[q].x = 0; v[q].y = 0; }
+            }
+            fft_forward<N>(v, t, tw, xb);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], ml[spec_index<N>(t, q)]);
+            fft_inverse<N>(v, t, tw, xb);
+            __syncthreads();                 // everyone finished reading the exchange buffer
+#pragma unroll
+            for (int q = 0; q < 16; ++q) xb.st(line_index<N>(t, q), v[q]);
         }
-        fft_forward<N>(v, t, tw, xb);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], ml[spec_index<N>(t, q)]);
-        fft_inverse<N>(v, t, tw, xb);
-#pragma unroll
-        for (int q = 0; q < 16; ++q) res[f][q] = v[q];
+        __syncthreads();
     }
-    if (!ok) return;
+    // ---------------- phase B: vectorised streaming update ----------------
+    constexpr int CG = W / V;                    // column groups
+    constexpr int RP = S::THREADS / CG;          // rows per pass
+    constexpr int NPASS = N / RP;
+    constexpr int PB = (NPASS % 2 == 0) ? 2 : 1; // passes whose loads are batched
+    const int cg = threadIdx.x % CG, tr = threadIdx.x / CG;
+    const int k = k0 + cg * V;
+    if (k >= p.nz) return;
     const unsigned mask = term_mask(p, i, i + 1, 0, p.ny, k0, k0 + W);
     const int in = i + p.dir;                       // x neighbour plane
     const bool nb_inside = (in >= 0 && in < p.nx);
-    const bool nb_halo = !nb_inside && p.halo[0] != nullptr;
+    const bool nb_any = nb_inside || p.halo[0] != nullptr;
+    const void* nFy = nb_inside ? p.F[1] : p.halo[0];
+    const void* nFz = nb_inside ? p.F[2] : p.halo[1];
+    const size_t nbase = nb_inside ? (size_t)in * plane : 0;
+    const double sx = p.dir > 0 ? p.rdx : -p.rdx;
+#pragma unroll 1
+    for (int pass0 = 0; pass0 < NPASS; pass0 += PB) {
+        A dz0[PB][V], dz1[PB][V], a3[PB][V], a4[PB][V], b3[PB][V], b4[PB][V], g[PB][3][V];
+        double cf[PB][V];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const int j = line_index<N>(t, q);
-        const size_t idx = pbase + (size_t)j * p.nz;
-        A d[6];
-        Conv<CPLX>::set(d[0], d[5], res, q);
-        d[1] = E::ld(p.dz[0], idx);
-        d[2] = E::ld(p.dz[1], idx);
-        if (p.pstd) {
-            d[3] = E::ld(p.dxs[0], idx);
-            d[4] = E::ld(p.dxs[1], idx);
-        } else if (nb_inside || nb_halo) {
-            const size_t nidx = nb_inside ? (size_t)in * plane + (size_t)j * p.nz + k
-                                          : (size_t)j * p.nz + k;
-            const void* Fy = nb_inside ? p.F[1] : p.halo[0];
-            const void* Fz = nb_inside ? p.F[2] : p.halo[1];
-            const double s = p.dir > 0 ? p.rdx : -p.rdx;
-            d[3] = a_scale(s, a_sub(E::ld(Fz, nidx), E::ld(p.F[2], idx)));
-            d[4] = a_scale(s, a_sub(E::ld(Fy, nidx), E::ld(p.F[1], idx)));
-        } else {
-            d[3] = a_zero(A());
-            d[4] = a_zero(A());
+        for (int u = 0; u < PB; ++u) {
+            const int j = tr + (pass0 + u) * RP;
+            const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
+            VV::ld(p.dz[0], idx, dz0[u]);
+            VV::ld(p.dz[1], idx, dz1[u]);
+            if (p.pstd) {
+                VV::ld(p.dxs[0], idx, a3[u]);
+                VV::ld(p.dxs[1], idx, a4[u]);
+            } else if (nb_any) {
+                const size_t nidx = nbase + (size_t)j * p.nz + k;
+                VV::ld(nFz, nidx, a3[u]);
+                VV::ld(nFy, nidx, a4[u]);
+                VV::ld(p.F[2], idx, b3[u]);
+                VV::ld(p.F[1], idx, b4[u]);
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) VV::ld(p.G[c], idx, g[u][c]);
+            ld_coeff<V>(p.C, idx, cf[u]);
         }
-        cell_update<T, CPLX>(p, mask, i, j, k, d);
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+            const int j = tr + (pass0 + u) * RP;
+            const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                A d[6];
+                const C r0 = xbuf[(size_t)j * W + cg * V + v];
+                if constexpr (CPLX) {
+                    const C r1 = xbuf[(size_t)N * W + (size_t)j * W + cg * V + v];
+                    d[0] = make_double2((double)r0.x, (double)r0.y);
+                    d[5] = make_double2((double)r1.x, (double)r1.y);
+                } else {
+                    d[0] = (double)r0.x; d[5] = (double)r0.y;
+                }
+                d[1] = dz0[u][v];
+                d[2] = dz1[u][v];
+                if (p.pstd) { d[3] = a3[u][v]; d[4] = a4[u][v]; }
+                else if (nb_any) {
+                    d[3] = a_scale(sx, a_sub(a3[u][v], b3[u][v]));
+                    d[4] = a_scale(sx, a_sub(a4[u][v], b4[u][v]));
+                } else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
+                A gg[3] = {g[u][0][v], g[u][1][v], g[u][2][v]};
+                cell_update_regs<T, CPLX>(p, mask, i, j, k + v, cf[u][v], d, gg);
+                g[u][0][v] = gg[0]; g[u][1][v] = gg[1]; g[u][2][v] = gg[2];
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) VV::st(p.G[c], idx, g[u][c]);
+        }
     }
 }
 
@@ -297,7 +334,7 @@ int launch_yline_update(Ctx* c, const UpdParams& p, int half) {
     if (p.i1 <= p.i0) return 0;
 #define Y_CASE(NN) {                                                                        \
         using S = SCfg<T, CPLX, NN>;                                                        \
-        size_t sm = sizeof(C) * (2 * NN + (size_t)NN * S::W);                               \
+        size_t sm = sizeof(C) * (2 * NN + (size_t)NN * S::W * Fld<T, CPLX>::NF);            \
         auto kern = k_yline_update<T, CPLX, NN>;                                            \
         if (set_smem(kern, sm)) return 1;                                                   \
         dim3 grid((unsigned)((c->cfg.nz + S::W - 1) / S::W), (unsigned)(p.i1 - p.i0));      \

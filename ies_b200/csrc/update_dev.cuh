@@ -59,39 +59,81 @@ __device__ __forceinline__ unsigned term_mask(const UpdParams& p, int i0, int i1
     return m;
 }
 
-// d[] = the six derivatives of this half-step at the cell, slot order IES_D_*:
+// Vector access: V = 16 bytes / element consecutive cells along z per thread.
+template <typename T, bool CPLX> struct Vec;
+template <> struct Vec<double, false> {
+    static constexpr int V = 2;
+    static __device__ __forceinline__ void ld(const void* p, size_t i, double (&o)[2]) {
+        const double2 v = *reinterpret_cast<const double2*>((const double*)p + i); o[0] = v.x; o[1] = v.y;
+    }
+    static __device__ __forceinline__ void st(void* p, size_t i, const double (&o)[2]) {
+        *reinterpret_cast<double2*>((double*)p + i) = make_double2(o[0], o[1]);
+    }
+};
+template <> struct Vec<float, false> {
+    static constexpr int V = 4;
+    static __device__ __forceinline__ void ld(const void* p, size_t i, double (&o)[4]) {
+        const float4 v = *reinterpret_cast<const float4*>((const float*)p + i);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    static __device__ __forceinline__ void st(void* p, size_t i, const double (&o)[4]) {
+        *reinterpret_cast<float4*>((float*)p + i) = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+    }
+};
+template <> struct Vec<float, true> {
+    static constexpr int V = 2;
+    static __device__ __forceinline__ void ld(const void* p, size_t i, double2 (&o)[2]) {
+        const float4 v = *reinterpret_cast<const float4*>((const float2*)p + i);
+        o[0] = make_double2(v.x, v.y); o[1] = make_double2(v.z, v.w);
+    }
+    static __device__ __forceinline__ void st(void* p, size_t i, const double2 (&o)[2]) {
+        *reinterpret_cast<float4*>((float2*)p + i) =
+            make_float4((float)o[0].x, (float)o[0].y, (float)o[1].x, (float)o[1].y);
+    }
+};
+template <> struct Vec<double, true> {
+    static constexpr int V = 1;
+    static __device__ __forceinline__ void ld(const void* p, size_t i, double2 (&o)[1]) { o[0] = ((const double2*)p)[i]; }
+    static __device__ __forceinline__ void st(void* p, size_t i, const double2 (&o)[1]) { ((double2*)p)[i] = o[0]; }
+};
+template <int V> __device__ __forceinline__ void ld_coeff(const double* p, size_t i, double (&o)[V]) {
+    if constexpr (V == 1) { o[0] = p[i]; }
+    else {
+#pragma unroll
+        for (int v = 0; v < V; v += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(p + i + v); o[v] = t.x; o[v + 1] = t.y;
+        }
+    }
+}
+
+// Update of the three components of one cell held in registers.
+//   d[] = the six derivatives of this half-step, slot order IES_D_*:
 //   comp x: d[0]-d[1]   comp y: d[2]-d[3]   comp z: d[4]-d[5]
+// A CPML term on component c always consumes one of that component's own two curl
+// derivatives (space.py:1153-1162 etc.), selected by the parity of its slot.
 template <typename T, bool CPLX>
-__device__ __forceinline__ void cell_update(const UpdParams& p, unsigned mask, int i, int j, int k,
-                                            const typename AccT<CPLX>::type (&d)[6]) {
+__device__ __forceinline__ void cell_update_regs(const UpdParams& p, unsigned mask, int i, int j, int k,
+                                                 const double C, const typename AccT<CPLX>::type (&d)[6],
+                                                 typename AccT<CPLX>::type (&g)[3]) {
     using A = typename AccT<CPLX>::type;
     using E = Elem<T, CPLX>;
-    const size_t idx = ((size_t)i * p.ny + j) * p.nz + k;
-    const double C = p.C[idx];
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        bool touched = false;
-        A g = a_zero(A());
-        if (in_box(p.box[c].lo, p.box[c].hi, i, j, k)) {
-            g = E::ld(p.G[c], idx);
-            g = a_add(g, a_scale(C, a_sub(d[2 * c], d[2 * c + 1])));
-            touched = true;
-        }
+        const A da = d[2 * c], db = d[2 * c + 1];
+        if (in_box(p.box[c].lo, p.box[c].hi, i, j, k))
+            g[c] = a_add(g[c], a_scale(C, a_sub(da, db)));
         unsigned m = mask;
         while (m) {
             const int t = __ffs(m) - 1;
             m &= m - 1;
             const PmlTermDev& q = p.terms[t];
             if (q.comp != c || !in_box(q.lo, q.hi, i, j, k)) continue;
-            if (!touched) { g = E::ld(p.G[c], idx); touched = true; }
             const int ax = q.axis;
             const int n = (ax == 0 ? i - q.lo[0] : ax == 1 ? j - q.lo[1] : k - q.lo[2]);
             const int pn = n + q.psi_off;
             const int p0 = ax == 0 ? pn : i, p1 = ax == 1 ? pn : j, p2 = ax == 2 ? pn : k;
             const size_t pidx = ((size_t)p0 * q.pdim[1] + p1) * q.pdim[2] + p2;
-            A dd = d[0];
-#pragma unroll
-            for (int s = 1; s < 6; ++s) if (q.diff == s) dd = d[s];
+            const A dd = (q.diff & 1) ? db : da;
             A psi = E::ld(q.psi, pidx);
             psi = a_add(a_scale(q.b[n], psi), a_scale(q.a[n], dd));
             // psi is stored in field precision and the rounded value is what the
@@ -99,10 +141,24 @@ __device__ __forceinline__ void cell_update(const UpdParams& p, unsigned mask, i
             E::st(q.psi, pidx, psi);
             psi = E::rnd(psi);
             const A corr = a_scale(C, a_add(a_scale(q.kf[n], dd), psi));
-            g = a_add(g, a_scale(q.sign, corr));
+            g[c] = a_add(g[c], a_scale(q.sign, corr));
         }
-        if (touched) E::st(p.G[c], idx, g);
     }
+}
+
+// Scalar per-cell variant (loads and stores the field itself).
+template <typename T, bool CPLX>
+__device__ __forceinline__ void cell_update(const UpdParams& p, unsigned mask, int i, int j, int k,
+                                            const typename AccT<CPLX>::type (&d)[6]) {
+    using A = typename AccT<CPLX>::type;
+    using E = Elem<T, CPLX>;
+    const size_t idx = ((size_t)i * p.ny + j) * p.nz + k;
+    A g[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = E::ld(p.G[c], idx);
+    cell_update_regs<T, CPLX>(p, mask, i, j, k, p.C[idx], d, g);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) E::st(p.G[c], idx, g[c]);
 }
 
 }  // namespace ies
