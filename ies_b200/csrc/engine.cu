@@ -6,6 +6,7 @@
 #include <cstring>
 #include <atomic>
 #include <algorithm>
+#include <cstdlib>
 
 #include "engine.h"
 #include "update_dev.cuh"
@@ -271,9 +272,49 @@ static int fill_params(ies_ctx* c, int half, UpdParams& p) {
     p.dir = half == IES_HALF_H ? +1 : -1;
     p.i0 = 0; p.i1 = c->cfg.nx;
     p.pstd = c->cfg.method == IES_PSTD;
+    p.dz_off = 0;
     p.rdx = 1.0 / c->cfg.dx; p.rdy = 1.0 / c->cfg.dy; p.rdz = 1.0 / c->cfg.dz;
     p.nterms = (int)c->terms[half].size();
     for (int t = 0; t < p.nterms; ++t) p.terms[t] = c->terms[half][t];
+    return 0;
+}
+
+static int ensure_scratch(ies_ctx* c, int first, int last) {
+    const size_t fbytes = (size_t)c->cfg.nx * c->cfg.ny * c->cfg.nz * c->esize;
+    for (int q = first; q <= last; ++q)
+        if (!c->scratch[q]) if (dev_alloc(c, &c->scratch[q], fbytes)) return 1;
+    return 0;
+}
+
+// Plan of the fused SHPF half-step (see k_shpf_fused): chunk size cx (a divisor of nx),
+// look-ahead la and the L2-resident scratch ring.
+static int ensure_fused_plan(ies_ctx* c) {
+    FusedPlan& fp = c->fused;
+    if (fp.ready) return 0;
+    const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
+    if (ny != nz || ny < 64 || ny > 512) return 0;
+    int cx = 8, la = 2;
+    if (const char* e = getenv("IES_B200_FUSED_CX")) cx = atoi(e);
+    if (const char* e = getenv("IES_B200_FUSED_LA")) la = atoi(e);
+    if (cx < 1) cx = 1;
+    if (cx > nx) cx = nx;
+    while (nx % cx) --cx;                      // all chunks full
+    if (la < 1) la = 1;
+    const int tt = ny / 16;
+    const int lpb = 256 / tt, w = 256 / tt;
+    fp.cx = cx; fp.la = la; fp.slots = la + 2;
+    fp.nc = nx / cx;
+    fp.kblocks = (nz + w - 1) / w;
+    fp.zitems_full = (cx * ny + lpb - 1) / lpb;
+    fp.total = fp.nc * (fp.zitems_full + cx * fp.kblocks);
+    void* ctr;
+    if (dev_alloc(c, &ctr, sizeof(int) * (size_t)(1 + 2 * fp.nc))) return 1;
+    fp.ctr = (int*)ctr;
+    const size_t rbytes = (size_t)fp.slots * cx * ny * nz * c->esize;
+    void* ring;
+    if (dev_alloc(c, &ring, 2 * rbytes)) return 1;      // one allocation: a single L2 window covers it
+    fp.ring[0] = ring; fp.ring[1] = (char*)ring + rbytes;
+    fp.ready = true;
     return 0;
 }
 
@@ -309,11 +350,36 @@ static int do_update(ies_ctx* c, int half) {
     }
     for (int a = 1; a < 3; ++a)
         if (!c->mult[half][a]) { set_error("spectral multiplier not set (malloc()/init_update_constants() missing)"); return 1; }
+    if (c->cfg.method == IES_SHPF && c->use_fused) {
+        if (ensure_fused_plan(c)) return 1;
+        const int r = launch_shpf_fused<T, CP>(c, p, half);
+        if (r != 2) return r;
+    }
+    if (c->cfg.method == IES_SHPF && c->chunk > 0 && c->chunk < nx) {
+        // x-chunked launch pairs: the z derivatives of one chunk live in a small scratch
+        // that is rewritten every chunk and stays resident in L2 between the two kernels
+        const int ch = c->chunk;
+        const size_t cbytes = (size_t)ch * ny * nz * c->esize;
+        for (int q = 0; q < 2; ++q)
+            if (!c->chunk_scratch[q]) if (dev_alloc(c, &c->chunk_scratch[q], cbytes)) return 1;
+        p.dz[0] = c->chunk_scratch[0]; p.dz[1] = c->chunk_scratch[1];
+        for (int i0 = 0; i0 < nx; i0 += ch) {
+            const int i1 = std::min(nx, i0 + ch);
+            if (launch_zline<T, CP>(c, p.F[1], p.F[0], c->chunk_scratch[0], c->chunk_scratch[1], half, i0, i1, 0)) return 1;
+            p.i0 = i0; p.i1 = i1;
+            p.dz_off = -(long long)i0 * ny * nz;
+            if (launch_yline_update<T, CP>(c, p, half)) return 1;
+        }
+        return 0;
+    }
+    if (ensure_scratch(c, 0, c->cfg.method == IES_PSTD ? 3 : 1)) return 1;
+    p.dz[0] = c->scratch[0]; p.dz[1] = c->scratch[1];
+    p.dxs[0] = c->scratch[2]; p.dxs[1] = c->scratch[3];
     if (c->cfg.method == IES_PSTD) {
         if (!c->mult[half][0]) { set_error("x multiplier not set"); return 1; }
         if (launch_xline<T, CP>(c, p.F[2], p.F[1], c->scratch[2], c->scratch[3], half)) return 1;
     }
-    if (launch_zline<T, CP>(c, p.F[1], p.F[0], c->scratch[0], c->scratch[1], half, 0, nx)) return 1;
+    if (launch_zline<T, CP>(c, p.F[1], p.F[0], c->scratch[0], c->scratch[1], half, 0, nx, 0)) return 1;
     if (launch_yline_update<T, CP>(c, p, half)) return 1;
     return 0;
 }
@@ -357,11 +423,13 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     for (int q = 0; q < 6; ++q) if (dev_alloc(c, &c->F[q], fbytes)) return 1;
     for (int h = 0; h < 2; ++h) { c->C[h] = nullptr; }
     for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
-    if (cfg->method != IES_FDTD) {
-        if (dev_alloc(c, &c->scratch[0], fbytes) || dev_alloc(c, &c->scratch[1], fbytes)) return 1;
-        if (cfg->method == IES_PSTD)
-            if (dev_alloc(c, &c->scratch[2], fbytes) || dev_alloc(c, &c->scratch[3], fbytes)) return 1;
-    }
+    // spectral scratch is allocated on first use (full size for the two-kernel path and for
+    // PSTD, a small L2-resident ring for the fused SHPF path)
+    c->use_fused = 0;
+    if (const char* e = getenv("IES_B200_FUSED")) c->use_fused = atoi(e);
+    c->chunk = 0;
+    if (const char* e = getenv("IES_B200_CHUNK")) c->chunk = atoi(e);
+    c->chunk_scratch[0] = c->chunk_scratch[1] = nullptr;
     const size_t pbytes = (size_t)cfg->ny * cfg->nz * c->esize;
     for (int h = 0; h < 2; ++h) for (int w = 0; w < 2; ++w) if (dev_alloc(c, &c->halo_recv[h][w], pbytes)) return 1;
     for (int h = 0; h < 2; ++h) for (int a = 0; a < 3; ++a) c->mult[h][a] = nullptr;

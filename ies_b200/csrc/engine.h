@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -35,10 +36,20 @@ struct UpdParams {
     int dir;                    // +1: forward differences (updateH); -1: backward (updateE)
     int i0, i1;                 // x range handled by this launch
     int pstd;                   // x derivative comes from dxs[]
+    long long dz_off;           // element offset of the dz scratch relative to the field index
     double rdx, rdy, rdz;
     Box box[3];
     int nterms;
     PmlTermDev terms[MAX_TERMS];
+};
+
+// Work plan of the fused persistent SHPF half-step (spectral.cuh: k_shpf_fused).
+struct FusedPlan {
+    bool ready = false;
+    int cx = 0, la = 0, slots = 0, nc = 0, kblocks = 0, zitems_full = 0, nsegs = 0, total = 0;
+    int* ctr = nullptr;        // 1 + 2*nc counters (device)
+    void* ring[2] = {nullptr, nullptr};   // z-derivative scratch ring: slots*cx planes each
+    int grid[2] = {0, 0};
 };
 
 struct Ctx {
@@ -63,6 +74,10 @@ struct Ctx {
     cudaEvent_t ev_t0, ev_t1;          // ies_timer_start/stop
     int profiling;                     // per-kernel CUDA-event timing on/off
     std::vector<cudaEvent_t> prof_ev[4][2];   // [slot][begin/end]
+    FusedPlan fused;
+    int use_fused;                     // 1: fused persistent SHPF half-step when applicable
+    int chunk;                         // x planes per (z-line, y-line) launch pair; 0 = whole slab
+    void* chunk_scratch[2];
 };
 
 enum { PROF_ZLINE = 0, PROF_YLINE_UPDATE = 1, PROF_XLINE = 2, PROF_FDTD = 3 };
@@ -76,11 +91,13 @@ void count_launch(int n = 1);
 // spectral_*.cu: z-line / strided-line derivative passes and the fused y-line update.
 // All return 0 or set the error and return 1.
 template <typename T, bool CPLX>
-int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int i0, int i1);
+int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int i0, int i1, int out_i0);
 template <typename T, bool CPLX>
 int launch_xline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half);
 template <typename T, bool CPLX>
 int launch_yline_update(Ctx* c, const UpdParams& p, int half);
+template <typename T, bool CPLX>
+int launch_shpf_fused(Ctx* c, const UpdParams& p, int half);
 
 bool fft_len_supported(int n);
 

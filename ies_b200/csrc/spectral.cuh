@@ -54,50 +54,81 @@ template <int N> struct ZCfg {
     static constexpr int THREADS = LPB * TT;
 };
 
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v; asm volatile("ld.global.acquire.gpu.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void red_release(int* p) {
+    asm volatile("red.global.release.gpu.add.s32 [%0], 1;" :: "l"(p) : "memory");
+}
+// thread 0 spins until *ctr >= need (no-op when ctr is null); callers follow with a CTA barrier
+__device__ __forceinline__ void wait_counter(const int* ctr, int need) {
+    if (need > 0 && threadIdx.x == 0) {
+        while (ld_acquire(ctr) < need) __nanosleep(32);
+    }
+}
+
+// One work item = LPB adjacent z lines.  Input lines start at in_line0 (+ item*LPB), the
+// derivative lines go to out_line0 (+ item*LPB) of the scratch arrays.
 template <typename T, bool CPLX, int N>
-__global__ void __launch_bounds__(ZCfg<N>::THREADS)
-k_zline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict__ dA,
-        void* __restrict__ dB, long line0, long nlines,
-        const typename Cx<T>::type* __restrict__ twg, const typename Cx<T>::type* __restrict__ mlg) {
+__device__ __forceinline__ void zline_item(const void* __restrict__ A, const void* __restrict__ B,
+                                           void* __restrict__ dA, void* __restrict__ dB,
+                                           long in_line0, long out_line0, long nlines, long item,
+                                           const typename Cx<T>::type* tw, const typename Cx<T>::type* ml,
+                                           typename Cx<T>::type* xbuf,
+                                           const int* dep_ctr = nullptr, int dep_need = 0) {
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
     constexpr int TT = ZCfg<N>::TT, LPB = ZCfg<N>::LPB;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C* tw = reinterpret_cast<C*>(smem_raw);
-    C* ml = tw + N;
-    C* xbuf = ml + N;
-    load_tables(tw, ml, twg, mlg, N);
     const int t = threadIdx.x % TT, l = threadIdx.x / TT;
-    const long line = (long)blockIdx.x * LPB + l;
+    const long line = item * LPB + l;
     const bool ok = line < nlines;
-    const size_t base = (size_t)(line0 + line) * N;
+    const size_t ibase = (size_t)(in_line0 + line) * N;
+    const size_t obase = (size_t)(out_line0 + line) * N;
     XchgContig<C, N> xb{xbuf + (size_t)l * XchgContig<C, N>::LS};
 #pragma unroll 1
     for (int f = 0; f < F::NF; ++f) {
         C v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            if (ok) v[q] = F::ld(A, B, base + line_index<N>(t, q), f);
+            if (ok) v[q] = F::ld(A, B, ibase + line_index<N>(t, q), f);
             else { v[q].x = 0; v[q].y = 0; }
         }
         fft_forward<N>(v, t, tw, xb);
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], ml[spec_index<N>(t, q)]);
         fft_inverse<N>(v, t, tw, xb);
+        if (dep_need > 0 && f == 0) {            // output slot free? (fused kernel only; CTA-uniform)
+            wait_counter(dep_ctr, dep_need);
+            __syncthreads();
+        }
         if (ok) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) F::st(dA, dB, base + line_index<N>(t, q), v[q], f);
+            for (int q = 0; q < 16; ++q) F::st(dA, dB, obase + line_index<N>(t, q), v[q], f);
         }
     }
+}
+
+template <typename T, bool CPLX, int N>
+__global__ void __launch_bounds__(ZCfg<N>::THREADS)
+k_zline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict__ dA,
+        void* __restrict__ dB, long line0, long oline0, long nlines,
+        const typename Cx<T>::type* __restrict__ twg, const typename Cx<T>::type* __restrict__ mlg) {
+    using C = typename Cx<T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* tw = reinterpret_cast<C*>(smem_raw);
+    C* ml = tw + N;
+    C* xbuf = ml + N;
+    load_tables(tw, ml, twg, mlg, N);
+    zline_item<T, CPLX, N>(A, B, dA, dB, line0, oline0, nlines, (long)blockIdx.x, tw, ml, xbuf);
 }
 
 // ------------------------------------------------------- strided lines (x) -----
 template <typename T, bool CPLX, int N> struct SCfg {
     static constexpr int TT = N / 16;
     static constexpr int ES = (int)sizeof(T) * (CPLX ? 2 : 1);
-    static constexpr int WMIN = 128 / ES;                         // one 128-byte segment per row
-    static constexpr int W = (128 / TT) > WMIN ? (128 / TT) : WMIN;
-    static constexpr int THREADS = W * TT;
+    static constexpr int THREADS = 256;
+    static constexpr int W = THREADS / TT;                        // adjacent lines (columns) per CTA
+    static_assert(W * ES >= 32, "row segment below one sector");
 };
 
 template <typename T, bool CPLX, int N>
@@ -143,10 +174,15 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 // Phase B: the CTA re-maps to 16-byte vectors along z (V cells per thread) and streams
 //          the cell update: PB row groups of loads are issued before any arithmetic so
 //          enough bytes are in flight to cover HBM latency.
-template <typename T, bool CPLX, int N>
-__global__ void __launch_bounds__(SCfg<T, CPLX, N>::THREADS, (SCfg<T, CPLX, N>::THREADS <= 256 ? 2 : 1))
-k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ twg,
-               const typename Cx<T>::type* __restrict__ mlg) {
+// One work item = the tile (plane i, columns kb*W .. kb*W+W-1, all rows).  dz_off is the
+// element offset added to a cell index when reading the z-derivative scratch (0 for
+// full-size scratch, ring-slot offset in the fused kernel); DZCG selects ld.global.cg
+// for those reads (data produced by other CTAs of the same launch).
+template <typename T, bool CPLX, int N, bool DZCG>
+__device__ __forceinline__ void yline_item(const UpdParams& p, const int i, const int kb, const long long dz_off,
+                                           const typename Cx<T>::type* tw, const typename Cx<T>::type* ml,
+                                           typename Cx<T>::type* xbuf,
+                                           const int* dep_ctr = nullptr, int dep_need = 0) {
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
     using A = typename AccT<CPLX>::type;
@@ -155,13 +191,7 @@ k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ twg,
     constexpr int W = S::W;
     constexpr int V = VV::V;
     constexpr int NF = F::NF;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C* tw = reinterpret_cast<C*>(smem_raw);
-    C* ml = tw + N;
-    C* xbuf = ml + N;                       // NF buffers of N*W: exchange, then derivative stash
-    load_tables(tw, ml, twg, mlg, N);
-    const int k0 = blockIdx.x * W;
-    const int i = p.i0 + blockIdx.y;
+    const int k0 = kb * W;
     const size_t plane = (size_t)p.ny * p.nz;
     {
         const int c = threadIdx.x % W, t = threadIdx.x / W;
@@ -186,6 +216,7 @@ k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ twg,
 #pragma unroll
             for (int q = 0; q < 16; ++q) xb.st(line_index<N>(t, q), v[q]);
         }
+        wait_counter(dep_ctr, dep_need);     // z derivatives of this chunk produced? (fused kernel only)
         __syncthreads();
     }
     // ---------------- phase B: vectorised streaming update ----------------
@@ -212,8 +243,8 @@ k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ twg,
         for (int u = 0; u < PB; ++u) {
             const int j = tr + (pass0 + u) * RP;
             const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
-            VV::ld(p.dz[0], idx, dz0[u]);
-            VV::ld(p.dz[1], idx, dz1[u]);
+            VV::template ldx<DZCG>(p.dz[0], (size_t)((long long)idx + dz_off), dz0[u]);
+            VV::template ldx<DZCG>(p.dz[1], (size_t)((long long)idx + dz_off), dz1[u]);
             if (p.pstd) {
                 VV::ld(p.dxs[0], idx, a3[u]);
                 VV::ld(p.dxs[1], idx, a4[u]);
@@ -260,6 +291,114 @@ k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ twg,
     }
 }
 
+template <typename T, bool CPLX, int N>
+__global__ void __launch_bounds__(256, (CPLX ? 1 : 2))
+k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ twg,
+               const typename Cx<T>::type* __restrict__ mlg, const int tables_in_smem) {
+    using C = typename Cx<T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // The twiddle / multiplier tables are read straight from global memory (L1-resident,
+    // 8 KB) by default: that keeps the CTA at N*W*16 B of shared memory, so two CTAs fit the
+    // 132 KB carve-out and 96 KB of L1 remain for loads in flight (measured: the kernel's
+    // bandwidth follows the L1 size left by the carve-out).
+    const C* tw = twg;
+    const C* ml = mlg;
+    C* xbuf = reinterpret_cast<C*>(smem_raw);      // NF buffers of N*W: exchange, then derivative stash
+    if (tables_in_smem) {
+        C* stw = reinterpret_cast<C*>(smem_raw);
+        C* sml = stw + N;
+        xbuf = sml + N;
+        load_tables(stw, sml, twg, mlg, N);
+        tw = stw; ml = sml;
+    }
+    yline_item<T, CPLX, N, false>(p, p.i0 + (int)blockIdx.y, (int)blockIdx.x, p.dz_off, tw, ml, xbuf);
+}
+
+// ------------------------------------------------ fused persistent half-step -----
+// SHPF half-step as ONE persistent launch: z-line items and y-line/update items are
+// pulled from a global queue ordered so that a chunk's z derivatives are produced two
+// groups before they are consumed; the scratch is a 3-chunk ring that stays resident in
+// the 126 MB L2, so the z derivatives never travel to HBM.  Dependencies are per-chunk
+// completion counters (release/acquire at gpu scope); an item is only claimed by a
+// running CTA and never waits on an item claimed later, so the scheme cannot deadlock.
+struct FusedArgs {
+    int total;
+    int* ctr;            // [0] queue head, [1 .. nc] z items done, [1+nc .. 2nc] y items done
+    int nc, cx, la;      // chunks, planes per chunk, look-ahead of the z items (chunks)
+    int slots;           // ring slots of the z-derivative scratch
+    int kblocks;         // y-line items per plane
+    int zitems_full;     // z items of a full chunk (cx*ny/LPB)
+    int debug_skip;      // development: 1 = skip y work, 2 = skip z work
+};
+
+
+template <typename T, bool CPLX, int N>
+__global__ void __launch_bounds__(256, (CPLX ? 1 : 2))
+k_shpf_fused(const UpdParams p, const FusedArgs fa,
+             const typename Cx<T>::type* __restrict__ twz, const typename Cx<T>::type* __restrict__ mlz,
+             const typename Cx<T>::type* __restrict__ twy, const typename Cx<T>::type* __restrict__ mly) {
+    using C = typename Cx<T>::type;
+    static_assert(ZCfg<N>::THREADS == 256 && SCfg<T, CPLX, N>::THREADS == 256, "fused kernel needs 256-thread items");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* tz = reinterpret_cast<C*>(smem_raw);
+    C* mz = tz + N;
+    C* ty = mz + N;
+    C* my = ty + N;
+    C* xbuf = my + N;
+    for (int q = threadIdx.x; q < N; q += blockDim.x) { tz[q] = twz[q]; mz[q] = mlz[q]; ty[q] = twy[q]; my[q] = mly[q]; }
+    __shared__ int s_item[2];
+    const size_t plane = (size_t)p.ny * p.nz;
+    // queue layout (all chunks are full: cx divides nx):
+    //   [z(0) .. z(la-1)] then for c = 0 .. nc-1: y(c), z(c+la) (z only while c+la < nc)
+    const int zf = fa.zitems_full, yf = fa.cx * fa.kblocks;
+    const int head = min(fa.la, fa.nc) * zf;
+    const int npair = max(fa.nc - fa.la, 0);            // chunks c that are followed by z(c+la)
+    if (threadIdx.x == 0) s_item[0] = atomicAdd(&fa.ctr[0], 1);
+    int par = 0;
+    while (true) {
+        __syncthreads();                       // s_item[par] visible; previous item done with smem
+        const int item = s_item[par];
+        if (item >= fa.total) break;
+        if (threadIdx.x == 0) s_item[par ^ 1] = atomicAdd(&fa.ctr[0], 1);   // prefetch the next claim
+        par ^= 1;
+        int type, c, local;
+        if (item < head) { type = 0; c = item / zf; local = item - c * zf; }
+        else {
+            const int r = item - head;
+            const int pairs_items = npair * (yf + zf);
+            if (r < pairs_items) {
+                const int pr = r / (yf + zf), w = r - pr * (yf + zf);
+                if (w < yf) { type = 1; c = pr; local = w; }
+                else { type = 0; c = pr + fa.la; local = w - yf; }
+            } else {
+                const int r2 = r - pairs_items;
+                type = 1; c = npair + r2 / yf; local = r2 - (r2 / yf) * yf;
+            }
+        }
+        const int pl0 = c * fa.cx;                                   // first plane of the chunk
+        const int slot = c % fa.slots;
+        if (type == 0) {
+            // the ring slot must have been consumed by the y items of chunk c-slots
+            if (fa.debug_skip == 2) { if (threadIdx.x == 0) red_release(&fa.ctr[1 + c]); continue; }
+            const bool wrap = c >= fa.slots;
+            const int* dep = &fa.ctr[wrap ? 1 + fa.nc + (c - fa.slots) : 0];
+            zline_item<T, CPLX, N>(p.F[1], p.F[0], const_cast<void*>(p.dz[0]), const_cast<void*>(p.dz[1]),
+                                   (long)pl0 * p.ny, (long)slot * fa.cx * p.ny, (long)fa.cx * p.ny, (long)local,
+                                   tz, mz, xbuf, dep, wrap ? yf : 0);
+            __syncthreads();
+            if (threadIdx.x == 0) { __threadfence(); red_release(&fa.ctr[1 + c]); }
+        } else {
+            if (fa.debug_skip == 1) { if (threadIdx.x == 0) red_release(&fa.ctr[1 + fa.nc + c]); continue; }
+            const int i = pl0 + local / fa.kblocks;
+            const int kb = local - (local / fa.kblocks) * fa.kblocks;
+            const long long dz_off = ((long long)slot * fa.cx - pl0) * (long long)plane;
+            yline_item<T, CPLX, N, true>(p, i, kb, dz_off, ty, my, xbuf, &fa.ctr[1 + c], zf);
+            __syncthreads();
+            if (threadIdx.x == 0) { __threadfence(); red_release(&fa.ctr[1 + fa.nc + c]); }
+        }
+    }
+}
+
 // ------------------------------------------------------------- launchers -----
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
@@ -280,11 +419,12 @@ static int set_smem(K kernel, size_t bytes) {
     }
 
 template <typename T, bool CPLX>
-int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int i0, int i1) {
+int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int i0, int i1, int out_i0) {
     using C = typename Cx<T>::type;
     const int n = c->cfg.nz;
     const long nlines = (long)(i1 - i0) * c->cfg.ny;
     const long line0 = (long)i0 * c->cfg.ny;
+    const long oline0 = (long)out_i0 * c->cfg.ny;
     if (nlines <= 0) return 0;
 #define Z_CASE(NN) {                                                                        \
         constexpr int LPB = ZCfg<NN>::LPB;                                                  \
@@ -292,7 +432,7 @@ int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
         auto kern = k_zline<T, CPLX, NN>;                                                   \
         if (set_smem(kern, sm)) return 1;                                                   \
         unsigned grid = (unsigned)((nlines + LPB - 1) / LPB);                               \
-        kern<<<grid, ZCfg<NN>::THREADS, sm, c->stream>>>(A, B, dA, dB, line0, nlines,        \
+        kern<<<grid, ZCfg<NN>::THREADS, sm, c->stream>>>(A, B, dA, dB, line0, oline0, nlines, \
             (const C*)c->tw[2], (const C*)c->mult[half][2]);                                \
     }
     prof_mark(c, PROF_ZLINE, 0);
@@ -332,19 +472,67 @@ int launch_yline_update(Ctx* c, const UpdParams& p, int half) {
     using C = typename Cx<T>::type;
     const int n = c->cfg.ny;
     if (p.i1 <= p.i0) return 0;
+    int tsm = 0;
+    if (const char* e = getenv("IES_B200_TABLES_SMEM")) tsm = atoi(e);
 #define Y_CASE(NN) {                                                                        \
         using S = SCfg<T, CPLX, NN>;                                                        \
-        size_t sm = sizeof(C) * (2 * NN + (size_t)NN * S::W * Fld<T, CPLX>::NF);            \
+        size_t sm = sizeof(C) * ((tsm ? 2 * NN : 0) + (size_t)NN * S::W * Fld<T, CPLX>::NF); \
         auto kern = k_yline_update<T, CPLX, NN>;                                            \
         if (set_smem(kern, sm)) return 1;                                                   \
         dim3 grid((unsigned)((c->cfg.nz + S::W - 1) / S::W), (unsigned)(p.i1 - p.i0));      \
         kern<<<grid, S::THREADS, sm, c->stream>>>(p, (const C*)c->tw[1],                     \
-            (const C*)c->mult[half][1]);                                                    \
+            (const C*)c->mult[half][1], tsm);                                               \
     }
     prof_mark(c, PROF_YLINE_UPDATE, 0);
     IES_FOR_N(n, Y_CASE)
     prof_mark(c, PROF_YLINE_UPDATE, 1);
 #undef Y_CASE
+    count_launch();
+    IES_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Returns 0 = launched, 1 = error, 2 = configuration not covered by the fused kernel.
+template <typename T, bool CPLX>
+int launch_shpf_fused(Ctx* c, const UpdParams& p, int half) {
+    using C = typename Cx<T>::type;
+    const int n = c->cfg.ny;
+    if (c->cfg.nz != n || n < 64 || n > 512) return 2;
+    FusedPlan& fp = c->fused;
+    if (!fp.ready) return 2;
+    FusedArgs fa;
+    fa.total = fp.total;
+    fa.ctr = fp.ctr; fa.nc = fp.nc; fa.cx = fp.cx; fa.la = fp.la; fa.slots = fp.slots; fa.kblocks = fp.kblocks; fa.zitems_full = fp.zitems_full;
+    fa.debug_skip = 0;
+    if (const char* e = getenv("IES_B200_FUSED_SKIP")) fa.debug_skip = atoi(e);
+    UpdParams q = p;
+    q.dz[0] = fp.ring[0]; q.dz[1] = fp.ring[1];
+    IES_CUDA(cudaMemsetAsync(fp.ctr, 0, sizeof(int) * (size_t)(1 + 2 * fp.nc), c->stream));
+    prof_mark(c, PROF_YLINE_UPDATE, 0);
+#define F_CASE(NN) {                                                                        \
+        using S = SCfg<T, CPLX, NN>;                                                        \
+        size_t xz = (size_t)ZCfg<NN>::LPB * XchgContig<C, NN>::LS;                          \
+        size_t xy = (size_t)NN * S::W * Fld<T, CPLX>::NF;                                   \
+        size_t sm = sizeof(C) * (4 * NN + (xz > xy ? xz : xy));                             \
+        auto kern = k_shpf_fused<T, CPLX, NN>;                                              \
+        if (set_smem(kern, sm)) return 1;                                                   \
+        if (fp.grid[half] == 0) {                                                           \
+            int per = 0, nsm = 0;                                                           \
+            IES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, 256, sm));   \
+            IES_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->cfg.device)); \
+            if (per < 1) { set_error("fused kernel does not fit on an SM"); return 1; }     \
+            fp.grid[half] = per * nsm;                                                      \
+        }                                                                                   \
+        kern<<<fp.grid[half], 256, sm, c->stream>>>(q, fa, (const C*)c->tw[2],               \
+            (const C*)c->mult[half][2], (const C*)c->tw[1], (const C*)c->mult[half][1]);    \
+    }
+    switch (n) {
+        case 64: F_CASE(64); break;   case 128: F_CASE(128); break;
+        case 256: F_CASE(256); break; case 512: F_CASE(512); break;
+        default: return 2;
+    }
+#undef F_CASE
+    prof_mark(c, PROF_YLINE_UPDATE, 1);
     count_launch();
     IES_CUDA(cudaGetLastError());
     return 0;

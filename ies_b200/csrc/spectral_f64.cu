@@ -1,7 +1,8 @@
 // Explicit instantiation of the spectral kernels for field dtype f64.
 #include "spectral.cuh"
 namespace ies {
-template int launch_zline<double, false>(Ctx*, const void*, const void*, void*, void*, int, int, int);
+template int launch_zline<double, false>(Ctx*, const void*, const void*, void*, void*, int, int, int, int);
 template int launch_xline<double, false>(Ctx*, const void*, const void*, void*, void*, int);
 template int launch_yline_update<double, false>(Ctx*, const UpdParams&, int);
+template int launch_shpf_fused<double, false>(Ctx*, const UpdParams&, int);
 }  // namespace ies

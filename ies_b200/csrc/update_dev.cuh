@@ -69,6 +69,10 @@ template <> struct Vec<double, false> {
     static __device__ __forceinline__ void st(void* p, size_t i, const double (&o)[2]) {
         *reinterpret_cast<double2*>((double*)p + i) = make_double2(o[0], o[1]);
     }
+    template <bool CG> static __device__ __forceinline__ void ldx(const void* p, size_t i, double (&o)[2]) {
+        if (CG) { const double2 v = __ldcg(reinterpret_cast<const double2*>((const double*)p + i)); o[0] = v.x; o[1] = v.y; }
+        else ld(p, i, o);
+    }
 };
 template <> struct Vec<float, false> {
     static constexpr int V = 4;
@@ -78,6 +82,11 @@ template <> struct Vec<float, false> {
     }
     static __device__ __forceinline__ void st(void* p, size_t i, const double (&o)[4]) {
         *reinterpret_cast<float4*>((float*)p + i) = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
+    }
+    template <bool CG> static __device__ __forceinline__ void ldx(const void* p, size_t i, double (&o)[4]) {
+        if (CG) { const float4 v = __ldcg(reinterpret_cast<const float4*>((const float*)p + i));
+                  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+        else ld(p, i, o);
     }
 };
 template <> struct Vec<float, true> {
@@ -90,11 +99,19 @@ template <> struct Vec<float, true> {
         *reinterpret_cast<float4*>((float2*)p + i) =
             make_float4((float)o[0].x, (float)o[0].y, (float)o[1].x, (float)o[1].y);
     }
+    template <bool CG> static __device__ __forceinline__ void ldx(const void* p, size_t i, double2 (&o)[2]) {
+        if (CG) { const float4 v = __ldcg(reinterpret_cast<const float4*>((const float2*)p + i));
+                  o[0] = make_double2(v.x, v.y); o[1] = make_double2(v.z, v.w); }
+        else ld(p, i, o);
+    }
 };
 template <> struct Vec<double, true> {
     static constexpr int V = 1;
     static __device__ __forceinline__ void ld(const void* p, size_t i, double2 (&o)[1]) { o[0] = ((const double2*)p)[i]; }
     static __device__ __forceinline__ void st(void* p, size_t i, const double2 (&o)[1]) { ((double2*)p)[i] = o[0]; }
+    template <bool CG> static __device__ __forceinline__ void ldx(const void* p, size_t i, double2 (&o)[1]) {
+        if (CG) o[0] = __ldcg((const double2*)p + i); else ld(p, i, o);
+    }
 };
 template <int V> __device__ __forceinline__ void ld_coeff(const double* p, size_t i, double (&o)[V]) {
     if constexpr (V == 1) { o[0] = p[i]; }

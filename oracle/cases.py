@@ -62,7 +62,18 @@ CASES = [
     _case('pstd_c64_xpml', 'PSTD', 'complex64', (32, 16, 16), src='plane'),
     _case('pstd_f64_nopml_hard', 'PSTD', 'float64', (16, 16, 32), pml=NOPML, src='point', put='hard'),
 ]
-CASES_BY_NAME = {k['name']: k for k in CASES}
+# Larger live-only cases (no golden file; compared with the oracle at test time).  ny = nz >= 64
+# exercises the fused persistent SHPF kernel including its scratch-ring wrap-around.
+LIVE_CASES = [
+    _case('shpf_f64_xpml_64', 'SHPF', 'float64', (40, 64, 64), steps=10, npml=6, pbc=PBC_YZ, bbc=NO),
+    _case('shpf_f64_allpml_64_r2', 'SHPF', 'float64', (40, 64, 64), steps=10, npml=6, pml=ALLPML, src='point', ranks=2),
+    _case('shpf_f32_allpml_64', 'SHPF', 'float32', (40, 64, 64), steps=10, npml=6, pml=ALLPML, src='point'),
+    _case('shpf_c64_xpml_64', 'SHPF', 'complex64', (40, 64, 64), steps=10, npml=6, pbc=PBC_YZ, bbc=NO),
+    _case('shpf_c128_bloch_yz_128', 'SHPF', 'complex128', (28, 128, 128), steps=6, bbc=BBC_YZ, pbc=NO, mmt=K1, src='point'),
+    _case('shpf_f64_xpml_16x64', 'SHPF', 'float64', (24, 16, 64), steps=10, pbc=PBC_YZ, bbc=NO),
+    _case('pstd_f64_xpml_64', 'PSTD', 'float64', (64, 32, 64), steps=8, npml=6, src='plane'),
+]
+CASES_BY_NAME = {k['name']: k for k in CASES + LIVE_CASES}
 
 
 def geometry(case):

@@ -24,11 +24,25 @@ def test_case_vs_reference_golden(product, name):
         assert np.asarray(got[n]).dtype == np.dtype(case['dtype'])
 
 
-@pytest.mark.parametrize('name', ['shpf_f64_xpml', 'fdtd_f64_allpml', 'pstd_f64_allpml'])
+@pytest.mark.parametrize('name', ['shpf_f64_xpml', 'fdtd_f64_allpml', 'pstd_f64_allpml'] +
+                         [k['name'] for k in C.LIVE_CASES])
 def test_case_vs_oracle_live(product, name):
     case = dict(C.CASES_BY_NAME[name])
-    case['steps'] = 17          # a step count no golden was generated for
+    if name in ('shpf_f64_xpml', 'fdtd_f64_allpml', 'pstd_f64_allpml'):
+        case['steps'] = 17          # a step count no golden was generated for
     got = H.run_product(product, case)
     want = C.run_oracle(case)
     errs = H.worst_rel_l2(got, want)
     assert max(errs.values()) <= H.tolerance(case), (name, errs)
+
+
+@pytest.mark.parametrize('name', ['shpf_f64_xpml_64', 'shpf_f64_allpml_64_r2', 'shpf_c64_xpml_64'])
+def test_two_kernel_path_matches_fused(product, name, monkeypatch):
+    """The fused persistent SHPF half-step and the two-kernel path give the same fields."""
+    case = C.CASES_BY_NAME[name]
+    monkeypatch.setenv('IES_B200_FUSED', '1')
+    a = H.run_product(product, case)
+    monkeypatch.setenv('IES_B200_FUSED', '0')
+    b = H.run_product(product, case)
+    for n in C.FIELDS:
+        assert np.array_equal(np.asarray(a[n]), np.asarray(b[n])), n
