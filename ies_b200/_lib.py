@@ -57,6 +57,7 @@ SIGNATURES = {
     'ies_destroy': (C.c_int, [_vp]),
     'ies_set_stream': (C.c_int, [_vp, _vp]),
     'ies_sync': (C.c_int, [_vp]),
+    'ies_set_option': (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     'ies_set_coeff': (C.c_int, [_vp, C.c_int, _dp, C.c_int64]),
     'ies_set_update_box': (C.c_int, [_vp, C.c_int, I3, I3]),
     'ies_set_multiplier': (C.c_int, [_vp, C.c_int, C.c_int, _dp, C.c_int32]),

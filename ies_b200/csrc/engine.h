@@ -29,6 +29,8 @@ struct UpdParams {
     const void* F[3];           // differentiated field (E in updateH, H in updateE): x,y,z
     void* G[3];                 // updated field
     const double* C;            // CH2 / CE2 (space.py:445-553, zero conductivity)
+    const uint8_t* Cidx;        // lossless palette form of C (<= 256 distinct values) or null:
+    const double* Cpal;         //   C[i] == Cpal[Cidx[i]] bit for bit; 1 B/cell of HBM traffic instead of 8
     const void* halo[2];        // neighbour planes of F_y, F_z (or null)
     const void* dz[2];          // scratch: d/dz F_y, d/dz F_x   (spectral methods)
     const void* dxs[2];         // scratch: d/dx F_z, d/dx F_y   (PSTD)
@@ -37,6 +39,7 @@ struct UpdParams {
     int i0, i1;                 // x range handled by this launch
     int pstd;                   // x derivative comes from dxs[]
     long long dz_off;           // element offset of the dz scratch relative to the field index
+    int pol_dz, pol_g;          // L2 eviction policy (mem_hint.cuh POL_*) of the scratch reads / G traffic
     double rdx, rdy, rdz;
     Box box[3];
     int nterms;
@@ -59,6 +62,10 @@ struct Ctx {
     cudaStream_t stream, own_stream;
     void* F[6];
     double* C[2];
+    uint8_t* Cidx[2];           // palette-compressed coefficients (valid when Cnpal > 0)
+    double* Cpal[2];
+    int Cnpal[2];
+    int use_palette;
     void* scratch[4];           // dzA dzB dxA dxB
     void* halo_recv[2][2];
     void* mult[2][3];           // [half][axis] complex table in FFT precision, pre-scaled by 1/N
@@ -78,8 +85,24 @@ struct Ctx {
     int use_fused;                     // 1: fused persistent SHPF half-step when applicable
     int chunk;                         // x planes per (z-line, y-line) launch pair; 0 = whole slab
     void* chunk_scratch[2];
+    int chunk_slots;                   // ring slots of the chunk scratch (two-stream pipeline)
+    int two_stream;                    // z-line kernels on a second stream, one chunk ahead
+    cudaStream_t zstream;
+    std::vector<cudaEvent_t> ev_z, ev_y;
+    cudaEvent_t ev_fork;
+    int pol_zin, pol_zout, pol_dz, pol_g;   // L2 eviction policies (mem_hint.cuh)
+    int l2_window;                     // cudaAccessPolicyWindow (persisting) on the chunk scratch
+    void* chunk_ring; size_t chunk_ring_bytes;
+    // alternating-orientation SHPF path (shpf_half.cuh): what the scratch pair currently holds
+    // and the x-range in which it is stale (fields written since it was produced)
+    int use_alt;
+    int scr_kind;                      // SCR_NONE / SCR_FOR_H (d/dy of E_z,E_x) / SCR_FOR_E (d/dz of H_y,H_x)
+    int scr_dirty_lo, scr_dirty_hi;
+    int use_graph;                     // replay the chunked half-step as a CUDA graph
+    cudaGraphExec_t graph_exec[2];
 };
 
+enum { SCR_NONE = 0, SCR_FOR_H = 1, SCR_FOR_E = 2 };
 enum { PROF_ZLINE = 0, PROF_YLINE_UPDATE = 1, PROF_XLINE = 2, PROF_FDTD = 3 };
 void prof_mark(Ctx* c, int slot, int end);
 
@@ -91,9 +114,12 @@ void count_launch(int n = 1);
 // spectral_*.cu: z-line / strided-line derivative passes and the fused y-line update.
 // All return 0 or set the error and return 1.
 template <typename T, bool CPLX>
-int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int i0, int i1, int out_i0);
+int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int i0, int i1, int out_i0,
+                 cudaStream_t st = nullptr);
 template <typename T, bool CPLX>
-int launch_xline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half);
+int launch_sline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int axis, int i0, int i1);
+template <typename T, bool CPLX>
+int launch_shpf_half(Ctx* c, const UpdParams& p, int half);
 template <typename T, bool CPLX>
 int launch_yline_update(Ctx* c, const UpdParams& p, int half);
 template <typename T, bool CPLX>

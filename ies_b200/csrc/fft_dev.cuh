@@ -185,6 +185,19 @@ template <typename C, int N> struct XchgContig {
         if (N / 16 <= 32) __syncwarp(); else __syncthreads();
     }
 };
+// Contiguous lines without padding: element i lives at i ^ ((i >> 4) & 15), which keeps both
+// the radix-16 scatter (16t + m) and the strided gather (t + 16m) conflict free while a line
+// occupies exactly N elements (the alternating-orientation kernel keeps its tile at 64 KB).
+template <typename C, int N> struct XchgContigSw {
+    C* base;
+    static constexpr int LS = N;
+    static __device__ __forceinline__ int phys(int i) { return i ^ ((i >> 4) & 15); }
+    __device__ __forceinline__ C ld(int i) const { return base[phys(i)]; }
+    __device__ __forceinline__ void st(int i, C v) const { base[phys(i)] = v; }
+    __device__ __forceinline__ void sync() const {
+        if (N / 16 <= 32) __syncwarp(); else __syncthreads();
+    }
+};
 // Strided lines (y or x axis): W adjacent lines per CTA, lane index = column.
 template <typename C, int W> struct XchgStrided {
     C* base;            // buffer + column

@@ -29,6 +29,12 @@ template <typename T> struct Fld<T, false> {
     static __device__ __forceinline__ void st(void* dA, void* dB, size_t i, C v, int) {
         ((T*)dA)[i] = v.x; ((T*)dB)[i] = v.y;
     }
+    template <bool HINT> static __device__ __forceinline__ C ldp(const void* A, const void* B, size_t i, int, uint64_t pol) {
+        C v; v.x = ld_pol<HINT>((const T*)A + i, pol); v.y = ld_pol<HINT>((const T*)B + i, pol); return v;
+    }
+    template <bool HINT> static __device__ __forceinline__ void stp(void* dA, void* dB, size_t i, C v, int, uint64_t pol) {
+        st_pol<HINT>((T*)dA + i, v.x, pol); st_pol<HINT>((T*)dB + i, v.y, pol);
+    }
 };
 template <typename T> struct Fld<T, true> {
     using C = typename Cx<T>::type;
@@ -38,6 +44,12 @@ template <typename T> struct Fld<T, true> {
     }
     static __device__ __forceinline__ void st(void* dA, void* dB, size_t i, C v, int f) {
         ((C*)(f == 0 ? dA : dB))[i] = v;
+    }
+    template <bool HINT> static __device__ __forceinline__ C ldp(const void* A, const void* B, size_t i, int f, uint64_t pol) {
+        return ld_pol<HINT>((const C*)(f == 0 ? A : B) + i, pol);
+    }
+    template <bool HINT> static __device__ __forceinline__ void stp(void* dA, void* dB, size_t i, C v, int f, uint64_t pol) {
+        st_pol<HINT>((C*)(f == 0 ? dA : dB) + i, v, pol);
     }
 };
 
@@ -69,13 +81,14 @@ __device__ __forceinline__ void wait_counter(const int* ctr, int need) {
 
 // One work item = LPB adjacent z lines.  Input lines start at in_line0 (+ item*LPB), the
 // derivative lines go to out_line0 (+ item*LPB) of the scratch arrays.
-template <typename T, bool CPLX, int N>
+template <typename T, bool CPLX, int N, bool HINT = false>
 __device__ __forceinline__ void zline_item(const void* __restrict__ A, const void* __restrict__ B,
                                            void* __restrict__ dA, void* __restrict__ dB,
                                            long in_line0, long out_line0, long nlines, long item,
                                            const typename Cx<T>::type* tw, const typename Cx<T>::type* ml,
                                            typename Cx<T>::type* xbuf,
-                                           const int* dep_ctr = nullptr, int dep_need = 0) {
+                                           const int* dep_ctr = nullptr, int dep_need = 0,
+                                           uint64_t pin = 0, uint64_t pout = 0) {
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
     constexpr int TT = ZCfg<N>::TT, LPB = ZCfg<N>::LPB;
@@ -90,7 +103,7 @@ __device__ __forceinline__ void zline_item(const void* __restrict__ A, const voi
         C v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            if (ok) v[q] = F::ld(A, B, ibase + line_index<N>(t, q), f);
+            if (ok) v[q] = F::template ldp<HINT>(A, B, ibase + line_index<N>(t, q), f, pin);
             else { v[q].x = 0; v[q].y = 0; }
         }
         fft_forward<N>(v, t, tw, xb);
@@ -103,23 +116,27 @@ __device__ __forceinline__ void zline_item(const void* __restrict__ A, const voi
         }
         if (ok) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) F::st(dA, dB, obase + line_index<N>(t, q), v[q], f);
+            for (int q = 0; q < 16; ++q) F::template stp<HINT>(dA, dB, obase + line_index<N>(t, q), v[q], f, pout);
         }
     }
 }
 
-template <typename T, bool CPLX, int N>
+template <typename T, bool CPLX, int N, bool HINT>
 __global__ void __launch_bounds__(ZCfg<N>::THREADS)
 k_zline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict__ dA,
         void* __restrict__ dB, long line0, long oline0, long nlines,
-        const typename Cx<T>::type* __restrict__ twg, const typename Cx<T>::type* __restrict__ mlg) {
+        const typename Cx<T>::type* __restrict__ twg, const typename Cx<T>::type* __restrict__ mlg,
+        const int pol_in, const int pol_out) {
     using C = typename Cx<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* tw = reinterpret_cast<C*>(smem_raw);
     C* ml = tw + N;
     C* xbuf = ml + N;
     load_tables(tw, ml, twg, mlg, N);
-    zline_item<T, CPLX, N>(A, B, dA, dB, line0, oline0, nlines, (long)blockIdx.x, tw, ml, xbuf);
+    uint64_t pin = 0, pout = 0;
+    if constexpr (HINT) { pin = make_policy(pol_in); pout = make_policy(pol_out); }
+    zline_item<T, CPLX, N, HINT>(A, B, dA, dB, line0, oline0, nlines, (long)blockIdx.x, tw, ml, xbuf,
+                                 nullptr, 0, pin, pout);
 }
 
 // ------------------------------------------------------- strided lines (x) -----
@@ -134,7 +151,7 @@ template <typename T, bool CPLX, int N> struct SCfg {
 template <typename T, bool CPLX, int N>
 __global__ void __launch_bounds__(SCfg<T, CPLX, N>::THREADS)
 k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict__ dA,
-        void* __restrict__ dB, long ncols, long stride,
+        void* __restrict__ dB, long ncols, long stride, long batch_stride,
         const typename Cx<T>::type* __restrict__ twg, const typename Cx<T>::type* __restrict__ mlg) {
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
@@ -147,13 +164,14 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
     const int c = threadIdx.x % W, t = threadIdx.x / W;
     const long col = (long)blockIdx.x * W + c;
     const bool ok = col < ncols;
+    const size_t boff = (size_t)blockIdx.y * (size_t)batch_stride;   // batch = one x-plane of y lines
     XchgStrided<C, W> xb{xbuf + c};
 #pragma unroll 1
     for (int f = 0; f < F::NF; ++f) {
         C v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            if (ok) v[q] = F::ld(A, B, (size_t)line_index<N>(t, q) * stride + col, f);
+            if (ok) v[q] = F::ld(A, B, boff + (size_t)line_index<N>(t, q) * stride + col, f);
             else { v[q].x = 0; v[q].y = 0; }
         }
         fft_forward<N>(v, t, tw, xb);
@@ -162,7 +180,7 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
         fft_inverse<N>(v, t, tw, xb);
         if (ok) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) F::st(dA, dB, (size_t)line_index<N>(t, q) * stride + col, v[q], f);
+            for (int q = 0; q < 16; ++q) F::st(dA, dB, boff + (size_t)line_index<N>(t, q) * stride + col, v[q], f);
         }
     }
 }
@@ -178,7 +196,7 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 // element offset added to a cell index when reading the z-derivative scratch (0 for
 // full-size scratch, ring-slot offset in the fused kernel); DZCG selects ld.global.cg
 // for those reads (data produced by other CTAs of the same launch).
-template <typename T, bool CPLX, int N, bool DZCG>
+template <typename T, bool CPLX, int N, bool DZCG, bool HINT = false>
 __device__ __forceinline__ void yline_item(const UpdParams& p, const int i, const int kb, const long long dz_off,
                                            const typename Cx<T>::type* tw, const typename Cx<T>::type* ml,
                                            typename Cx<T>::type* xbuf,
@@ -235,6 +253,8 @@ __device__ __forceinline__ void yline_item(const UpdParams& p, const int i, cons
     const void* nFz = nb_inside ? p.F[2] : p.halo[1];
     const size_t nbase = nb_inside ? (size_t)in * plane : 0;
     const double sx = p.dir > 0 ? p.rdx : -p.rdx;
+    uint64_t pdz = 0, pg = 0;
+    if constexpr (HINT) { pdz = make_policy(p.pol_dz); pg = make_policy(p.pol_g); }
 #pragma unroll 1
     for (int pass0 = 0; pass0 < NPASS; pass0 += PB) {
         A dz0[PB][V], dz1[PB][V], a3[PB][V], a4[PB][V], b3[PB][V], b4[PB][V], g[PB][3][V];
@@ -243,8 +263,13 @@ __device__ __forceinline__ void yline_item(const UpdParams& p, const int i, cons
         for (int u = 0; u < PB; ++u) {
             const int j = tr + (pass0 + u) * RP;
             const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
-            VV::template ldx<DZCG>(p.dz[0], (size_t)((long long)idx + dz_off), dz0[u]);
-            VV::template ldx<DZCG>(p.dz[1], (size_t)((long long)idx + dz_off), dz1[u]);
+            if constexpr (DZCG) {
+                VV::template ldx<true>(p.dz[0], (size_t)((long long)idx + dz_off), dz0[u]);
+                VV::template ldx<true>(p.dz[1], (size_t)((long long)idx + dz_off), dz1[u]);
+            } else {
+                VV::template ldp<HINT>(p.dz[0], (size_t)((long long)idx + dz_off), dz0[u], pdz);
+                VV::template ldp<HINT>(p.dz[1], (size_t)((long long)idx + dz_off), dz1[u], pdz);
+            }
             if (p.pstd) {
                 VV::ld(p.dxs[0], idx, a3[u]);
                 VV::ld(p.dxs[1], idx, a4[u]);
@@ -256,8 +281,8 @@ __device__ __forceinline__ void yline_item(const UpdParams& p, const int i, cons
                 VV::ld(p.F[1], idx, b4[u]);
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) VV::ld(p.G[c], idx, g[u][c]);
-            ld_coeff<V>(p.C, idx, cf[u]);
+            for (int c = 0; c < 3; ++c) VV::template ldp<HINT>(p.G[c], idx, g[u][c], pg);
+            ld_coeff<V>(p, idx, cf[u]);
         }
 #pragma unroll
         for (int u = 0; u < PB; ++u) {
@@ -286,12 +311,12 @@ __device__ __forceinline__ void yline_item(const UpdParams& p, const int i, cons
                 g[u][0][v] = gg[0]; g[u][1][v] = gg[1]; g[u][2][v] = gg[2];
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) VV::st(p.G[c], idx, g[u][c]);
+            for (int c = 0; c < 3; ++c) VV::template stp<HINT>(p.G[c], idx, g[u][c], pg);
         }
     }
 }
 
-template <typename T, bool CPLX, int N>
+template <typename T, bool CPLX, int N, bool HINT>
 __global__ void __launch_bounds__(256, (CPLX ? 1 : 2))
 k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ twg,
                const typename Cx<T>::type* __restrict__ mlg, const int tables_in_smem) {
@@ -311,7 +336,7 @@ k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ twg,
         load_tables(stw, sml, twg, mlg, N);
         tw = stw; ml = sml;
     }
-    yline_item<T, CPLX, N, false>(p, p.i0 + (int)blockIdx.y, (int)blockIdx.x, p.dz_off, tw, ml, xbuf);
+    yline_item<T, CPLX, N, false, HINT>(p, p.i0 + (int)blockIdx.y, (int)blockIdx.x, p.dz_off, tw, ml, xbuf);
 }
 
 // ------------------------------------------------ fused persistent half-step -----
@@ -419,8 +444,11 @@ static int set_smem(K kernel, size_t bytes) {
     }
 
 template <typename T, bool CPLX>
-int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int i0, int i1, int out_i0) {
+int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int i0, int i1, int out_i0,
+                 cudaStream_t st) {
     using C = typename Cx<T>::type;
+    if (!st) st = c->stream;
+    const bool hint = (c->pol_zin | c->pol_zout) != 0;
     const int n = c->cfg.nz;
     const long nlines = (long)(i1 - i0) * c->cfg.ny;
     const long line0 = (long)i0 * c->cfg.ny;
@@ -429,34 +457,46 @@ int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
 #define Z_CASE(NN) {                                                                        \
         constexpr int LPB = ZCfg<NN>::LPB;                                                  \
         size_t sm = sizeof(C) * (2 * NN + (size_t)LPB * XchgContig<C, NN>::LS);             \
-        auto kern = k_zline<T, CPLX, NN>;                                                   \
+        auto kern = hint ? k_zline<T, CPLX, NN, true> : k_zline<T, CPLX, NN, false>;        \
         if (set_smem(kern, sm)) return 1;                                                   \
         unsigned grid = (unsigned)((nlines + LPB - 1) / LPB);                               \
-        kern<<<grid, ZCfg<NN>::THREADS, sm, c->stream>>>(A, B, dA, dB, line0, oline0, nlines, \
-            (const C*)c->tw[2], (const C*)c->mult[half][2]);                                \
+        kern<<<grid, ZCfg<NN>::THREADS, sm, st>>>(A, B, dA, dB, line0, oline0, nlines,       \
+            (const C*)c->tw[2], (const C*)c->mult[half][2], c->pol_zin, c->pol_zout);       \
     }
-    prof_mark(c, PROF_ZLINE, 0);
+    if (st == c->stream) prof_mark(c, PROF_ZLINE, 0);
     IES_FOR_N(n, Z_CASE)
-    prof_mark(c, PROF_ZLINE, 1);
+    if (st == c->stream) prof_mark(c, PROF_ZLINE, 1);
 #undef Z_CASE
     count_launch();
     IES_CUDA(cudaGetLastError());
     return 0;
 }
 
+// Strided-line derivative of the pair (A, B): axis 0 = x lines of the whole slab (PSTD),
+// axis 1 = y lines of the x-planes [i0, i1) (refresh of the alternating SHPF path's scratch).
 template <typename T, bool CPLX>
-int launch_xline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half) {
+int launch_sline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int axis, int i0, int i1) {
     using C = typename Cx<T>::type;
-    const int n = c->cfg.nx;
-    const long ncols = (long)c->cfg.ny * c->cfg.nz;
+    const size_t es = sizeof(T) * (CPLX ? 2 : 1);
+    const long plane = (long)c->cfg.ny * c->cfg.nz;
+    const int n = axis == 0 ? c->cfg.nx : c->cfg.ny;
+    const long ncols = axis == 0 ? plane : (long)c->cfg.nz;
+    const long stride = ncols;
+    const long batch_stride = axis == 0 ? 0 : plane;
+    const unsigned batches = axis == 0 ? 1u : (unsigned)(i1 - i0);
+    if (axis == 1) {
+        if (i1 <= i0) return 0;
+        const size_t off = (size_t)i0 * plane * es;
+        A = (const char*)A + off; B = (const char*)B + off; dA = (char*)dA + off; dB = (char*)dB + off;
+    }
 #define X_CASE(NN) {                                                                        \
         using S = SCfg<T, CPLX, NN>;                                                        \
         size_t sm = sizeof(C) * (2 * NN + (size_t)NN * S::W);                               \
         auto kern = k_xline<T, CPLX, NN>;                                                   \
         if (set_smem(kern, sm)) return 1;                                                   \
-        unsigned grid = (unsigned)((ncols + S::W - 1) / S::W);                              \
-        kern<<<grid, S::THREADS, sm, c->stream>>>(A, B, dA, dB, ncols, ncols,                \
-            (const C*)c->tw[0], (const C*)c->mult[half][0]);                                \
+        dim3 grid((unsigned)((ncols + S::W - 1) / S::W), batches);                          \
+        kern<<<grid, S::THREADS, sm, c->stream>>>(A, B, dA, dB, ncols, stride, batch_stride, \
+            (const C*)c->tw[axis], (const C*)c->mult[half][axis]);                          \
     }
     prof_mark(c, PROF_XLINE, 0);
     IES_FOR_N(n, X_CASE)
@@ -472,12 +512,13 @@ int launch_yline_update(Ctx* c, const UpdParams& p, int half) {
     using C = typename Cx<T>::type;
     const int n = c->cfg.ny;
     if (p.i1 <= p.i0) return 0;
+    const bool hint = (p.pol_dz | p.pol_g) != 0;
     int tsm = 0;
     if (const char* e = getenv("IES_B200_TABLES_SMEM")) tsm = atoi(e);
 #define Y_CASE(NN) {                                                                        \
         using S = SCfg<T, CPLX, NN>;                                                        \
         size_t sm = sizeof(C) * ((tsm ? 2 * NN : 0) + (size_t)NN * S::W * Fld<T, CPLX>::NF); \
-        auto kern = k_yline_update<T, CPLX, NN>;                                            \
+        auto kern = hint ? k_yline_update<T, CPLX, NN, true> : k_yline_update<T, CPLX, NN, false>; \
         if (set_smem(kern, sm)) return 1;                                                   \
         dim3 grid((unsigned)((c->cfg.nz + S::W - 1) / S::W), (unsigned)(p.i1 - p.i0));      \
         kern<<<grid, S::THREADS, sm, c->stream>>>(p, (const C*)c->tw[1],                     \

@@ -2,6 +2,7 @@
 // (space.py:801-825, 1017-1037 main update; 1110-1712 CPML faces).
 #pragma once
 #include "engine.h"
+#include "mem_hint.cuh"
 
 namespace ies {
 
@@ -73,6 +74,12 @@ template <> struct Vec<double, false> {
         if (CG) { const double2 v = __ldcg(reinterpret_cast<const double2*>((const double*)p + i)); o[0] = v.x; o[1] = v.y; }
         else ld(p, i, o);
     }
+    template <bool HINT> static __device__ __forceinline__ void ldp(const void* p, size_t i, double (&o)[2], uint64_t pol) {
+        const double2 v = ld_pol<HINT>(reinterpret_cast<const double2*>((const double*)p + i), pol); o[0] = v.x; o[1] = v.y;
+    }
+    template <bool HINT> static __device__ __forceinline__ void stp(void* p, size_t i, const double (&o)[2], uint64_t pol) {
+        st_pol<HINT>(reinterpret_cast<double2*>((double*)p + i), make_double2(o[0], o[1]), pol);
+    }
 };
 template <> struct Vec<float, false> {
     static constexpr int V = 4;
@@ -87,6 +94,13 @@ template <> struct Vec<float, false> {
         if (CG) { const float4 v = __ldcg(reinterpret_cast<const float4*>((const float*)p + i));
                   o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
         else ld(p, i, o);
+    }
+    template <bool HINT> static __device__ __forceinline__ void ldp(const void* p, size_t i, double (&o)[4], uint64_t pol) {
+        const float4 v = ld_pol<HINT>(reinterpret_cast<const float4*>((const float*)p + i), pol);
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    template <bool HINT> static __device__ __forceinline__ void stp(void* p, size_t i, const double (&o)[4], uint64_t pol) {
+        st_pol<HINT>(reinterpret_cast<float4*>((float*)p + i), make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]), pol);
     }
 };
 template <> struct Vec<float, true> {
@@ -104,6 +118,14 @@ template <> struct Vec<float, true> {
                   o[0] = make_double2(v.x, v.y); o[1] = make_double2(v.z, v.w); }
         else ld(p, i, o);
     }
+    template <bool HINT> static __device__ __forceinline__ void ldp(const void* p, size_t i, double2 (&o)[2], uint64_t pol) {
+        const float4 v = ld_pol<HINT>(reinterpret_cast<const float4*>((const float2*)p + i), pol);
+        o[0] = make_double2(v.x, v.y); o[1] = make_double2(v.z, v.w);
+    }
+    template <bool HINT> static __device__ __forceinline__ void stp(void* p, size_t i, const double2 (&o)[2], uint64_t pol) {
+        st_pol<HINT>(reinterpret_cast<float4*>((float2*)p + i),
+               make_float4((float)o[0].x, (float)o[0].y, (float)o[1].x, (float)o[1].y), pol);
+    }
 };
 template <> struct Vec<double, true> {
     static constexpr int V = 1;
@@ -112,8 +134,30 @@ template <> struct Vec<double, true> {
     template <bool CG> static __device__ __forceinline__ void ldx(const void* p, size_t i, double2 (&o)[1]) {
         if (CG) o[0] = __ldcg((const double2*)p + i); else ld(p, i, o);
     }
+    template <bool HINT> static __device__ __forceinline__ void ldp(const void* p, size_t i, double2 (&o)[1], uint64_t pol) {
+        o[0] = ld_pol<HINT>((const double2*)p + i, pol);
+    }
+    template <bool HINT> static __device__ __forceinline__ void stp(void* p, size_t i, const double2 (&o)[1], uint64_t pol) {
+        st_pol<HINT>((double2*)p + i, o[0], pol);
+    }
 };
-template <int V> __device__ __forceinline__ void ld_coeff(const double* p, size_t i, double (&o)[V]) {
+// Coefficients of V consecutive cells: from the palette form (one index byte per cell, the
+// 2 KB palette stays in L1) when present, else from the f64 array.
+template <int V> __device__ __forceinline__ void ld_coeff(const UpdParams& q, size_t i, double (&o)[V]) {
+    if (q.Cidx != nullptr) {
+        if constexpr (V == 1) { o[0] = __ldg(q.Cpal + q.Cidx[i]); }
+        else if constexpr (V == 2) {
+            const unsigned short w = *reinterpret_cast<const unsigned short*>(q.Cidx + i);
+            o[0] = __ldg(q.Cpal + (w & 0xff)); o[1] = __ldg(q.Cpal + (w >> 8));
+        } else {
+            static_assert(V == 1 || V == 2 || V == 4, "vector width");
+            const unsigned w = *reinterpret_cast<const unsigned*>(q.Cidx + i);
+#pragma unroll
+            for (int v = 0; v < V; ++v) o[v] = __ldg(q.Cpal + ((w >> (8 * v)) & 0xff));
+        }
+        return;
+    }
+    const double* p = q.C;
     if constexpr (V == 1) { o[0] = p[i]; }
     else {
 #pragma unroll
@@ -173,7 +217,9 @@ __device__ __forceinline__ void cell_update(const UpdParams& p, unsigned mask, i
     A g[3];
 #pragma unroll
     for (int c = 0; c < 3; ++c) g[c] = E::ld(p.G[c], idx);
-    cell_update_regs<T, CPLX>(p, mask, i, j, k, p.C[idx], d, g);
+    double cf[1];
+    ld_coeff<1>(p, idx, cf);
+    cell_update_regs<T, CPLX>(p, mask, i, j, k, cf[0], d, g);
 #pragma unroll
     for (int c = 0; c < 3; ++c) E::st(p.G[c], idx, g[c]);
 }

@@ -73,6 +73,11 @@ int ies_destroy(ies_ctx* ctx);
  * stream = 0 restores the context's own stream. */
 int ies_set_stream(ies_ctx* ctx, void* cuda_stream);
 int ies_sync(ies_ctx* ctx);
+/* Engine tuning knobs (no reference counterpart; defaults need no call).  Names:
+ * "chunk" (x planes per z-line / y-line launch pair of the SHPF half-step, 0 = whole slab),
+ * "chunk_slots", "two_stream", "graph", "l2_window", "pol_zin", "pol_zout", "pol_dz",
+ * "pol_g" (L2 eviction policy: 0 none, 1 evict_last, 2 evict_first), "fused", "l2_reset". */
+int ies_set_option(ies_ctx* ctx, const char* name, int64_t value);
 
 /* ---- setup --------------------------------------------------------------- */
 /* init_update_constants (space.py:445-553) with zero conductivity: one f64

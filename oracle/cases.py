@@ -72,6 +72,13 @@ LIVE_CASES = [
     _case('shpf_c128_bloch_yz_128', 'SHPF', 'complex128', (28, 128, 128), steps=6, bbc=BBC_YZ, pbc=NO, mmt=K1, src='point'),
     _case('shpf_f64_xpml_16x64', 'SHPF', 'float64', (24, 16, 64), steps=10, pbc=PBC_YZ, bbc=NO),
     _case('pstd_f64_xpml_64', 'PSTD', 'float64', (64, 32, 64), steps=8, npml=6, src='plane'),
+    # sources on the components whose derivative the alternating SHPF path precomputes one
+    # half-step early (E_z, E_x before updateH; H_y, H_x before updateE): scratch refresh
+    _case('shpf_f64_src_ez', 'SHPF', 'float64', (24, 32, 32), steps=10, pbc=PBC_YZ, bbc=NO, src='point', src_field='Ez'),
+    _case('shpf_f64_src_ex_hard', 'SHPF', 'float64', (24, 32, 32), steps=10, pml=ALLPML, src='point', src_field='Ex', put='hard'),
+    _case('shpf_f64_src_hy_r2', 'SHPF', 'float64', (24, 32, 32), steps=10, pbc=PBC_YZ, bbc=NO, src='point', src_field='Hy', ranks=2),
+    _case('shpf_c128_src_hx_bloch', 'SHPF', 'complex128', (24, 32, 16), steps=10, bbc=BBC_YZ, pbc=NO, mmt=K1, src='point', src_field='Hx'),
+    _case('shpf_f32_src_ez_plane', 'SHPF', 'float32', (24, 16, 64), steps=10, pbc=PBC_YZ, bbc=NO, src='plane', src_field='Ez'),
 ]
 CASES_BY_NAME = {k['name']: k for k in CASES + LIVE_CASES}
 

@@ -1,0 +1,133 @@
+#!/usr/bin/env python
+"""Kernel experiments on the headline workload (development tool, GPU box only).
+
+    python tools/kexp.py [--nx 1024] [--steps 10] [--warmup 3] [--only NAME[,NAME]] [--list]
+
+Runs the bench workload of bench.py under several engine option sets
+(ies_set_option) in ONE process, re-uploading the same initial fields before each
+variant, and prints ms/step, Gcell/s and whether the result is bit-identical to the
+default path.  Under ncu use --only NAME --steps 1 --warmup 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+HINT_SCRATCH = dict(pol_zout=1, pol_dz=1)
+VARIANTS = [
+    ('base', {}),
+    ('chunk18', dict(chunk=18)),
+    ('chunk37', dict(chunk=37)),
+    ('chunk18_hs', dict(chunk=18, **HINT_SCRATCH)),
+    ('chunk37_hs', dict(chunk=37, **HINT_SCRATCH)),
+    ('chunk18_hs_g2', dict(chunk=18, pol_g=2, **HINT_SCRATCH)),
+    ('chunk18_hs_zin', dict(chunk=18, pol_zin=1, **HINT_SCRATCH)),
+    ('chunk18_win', dict(chunk=18, l2_window=1)),
+    ('chunk37_win', dict(chunk=37, l2_window=1)),
+    ('ts18', dict(chunk=18, two_stream=1, chunk_slots=3)),
+    ('ts18_graph', dict(chunk=18, two_stream=1, chunk_slots=3, graph=1)),
+    ('ts18_graph_hs', dict(chunk=18, two_stream=1, chunk_slots=3, graph=1, **HINT_SCRATCH)),
+    ('ts18_graph_hs_g2', dict(chunk=18, two_stream=1, chunk_slots=3, graph=1, pol_g=2, **HINT_SCRATCH)),
+    ('ts18_graph_hs_zin', dict(chunk=18, two_stream=1, chunk_slots=3, graph=1, pol_zin=1, **HINT_SCRATCH)),
+    ('ts18_graph_win', dict(chunk=18, two_stream=1, chunk_slots=3, graph=1, l2_window=1)),
+    ('ts9_graph_hs', dict(chunk=9, two_stream=1, chunk_slots=4, graph=1, **HINT_SCRATCH)),
+    ('ts37_graph_hs', dict(chunk=37, two_stream=1, chunk_slots=2, graph=1, **HINT_SCRATCH)),
+    ('ts37_graph_win', dict(chunk=37, two_stream=1, chunk_slots=2, graph=1, l2_window=1)),
+    ('hints_only_g2', dict(pol_g=2)),
+]
+ALL_OPTS = ('chunk', 'chunk_slots', 'two_stream', 'graph', 'l2_window', 'pol_zin', 'pol_zout', 'pol_dz', 'pol_g')
+DEFAULTS = dict(chunk=0, chunk_slots=3, two_stream=0, graph=0, l2_window=0, pol_zin=0, pol_zout=0, pol_dz=0, pol_g=0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--nx', type=int, default=1024)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--only', default='')
+    ap.add_argument('--list', action='store_true')
+    ap.add_argument('--check-steps', type=int, default=2)
+    args = ap.parse_args()
+    if args.list:
+        for n, o in VARIANTS: print(n, o)
+        return
+    import ies_b200
+    from ies_b200 import _lib
+    lib = _lib.load()
+    ns = types.SimpleNamespace(space=ies_b200.space, source=ies_b200.source,
+                               structure=ies_b200.structure, collector=ies_b200.collector)
+    bench.NX_PER_GPU = args.nx
+    sp, setter, src = bench.build_space(ns, args.nx, 100000)
+    sp.init_update_constants()
+    rng = np.random.default_rng(7)
+    init = {n: rng.uniform(-1, 1, sp.loc_grid) for n in ('Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz')}
+    ncell = sp.myNx * bench.NY * bench.NZ
+
+    def upload():
+        for n, a in init.items():
+            _lib.check(lib.ies_set_field(sp._ctx, _lib.COMP[n], _lib.I3(0, 0, 0), _lib.I3(*sp.loc_grid),
+                                         a.ctypes.data_as(C.c_void_p)))
+
+    def setopts(o):
+        full = dict(DEFAULTS); full.update(o)
+        for k in ALL_OPTS:
+            _lib.check(lib.ies_set_option(sp._ctx, k.encode(), int(full[k])))
+
+    def step(t):
+        setter.put_src('Ey', src.pulse_re(t), 'soft')
+        sp.updateH(t)
+        sp.updateE(t)
+
+    def signature():
+        out = []
+        for n in ('Ey', 'Hz', 'Ex'):
+            for i in (0, 5, sp.myNx // 2, sp.myNx - 1):
+                out.append(np.asarray(getattr(sp, n)[i, :, :]).copy())
+        return np.stack(out)
+
+    only = [x for x in args.only.split(',') if x]
+    ref_sig = None
+    rows = []
+    for name, o in VARIANTS:
+        if only and name not in only and name != 'base':
+            continue
+        try:
+            setopts(o)
+            sig_ok = None
+            if args.check_steps > 0:
+                upload()
+                for t in range(args.check_steps): step(t)
+                sp.sync()
+                sig = signature()
+                if name == 'base': ref_sig = sig
+                sig_ok = bool(np.array_equal(sig, ref_sig)) if ref_sig is not None else None
+            for t in range(args.warmup): step(t)
+            sp.sync()
+            _lib.check(lib.ies_timer_start(sp._ctx))
+            for t in range(args.steps): step(t)
+            ms = C.c_double()
+            _lib.check(lib.ies_timer_stop(sp._ctx, C.byref(ms)))
+            sp.sync()
+            per = ms.value / max(args.steps, 1)
+            row = dict(name=name, ms_per_step=round(per, 4), gcell_s=round(ncell / per / 1e6, 2) if per > 0 else None,
+                       bit_identical=sig_ok, opts=o)
+        except Exception as e:      # keep sweeping
+            row = dict(name=name, error=str(e), opts=o)
+        rows.append(row)
+        print(json.dumps(row), flush=True)
+    setopts({})
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    with open(os.path.join(ROOT, 'gpurun_out', 'kexp.json'), 'w') as f:
+        json.dump(rows, f, indent=1)
+
+
+if __name__ == '__main__':
+    main()
