@@ -29,7 +29,7 @@ bool fft_len_supported(int n) { return n >= 16 && n <= 512 && (n & (n - 1)) == 0
 // ------------------------------------------------------------------ FDTD -----
 // Yee curl with two-point differences (space.py:760-779, 975-994) + the fused
 // update/CPML of update_dev.cuh.  One thread per cell, z fastest (coalesced).
-template <typename T, bool CPLX>
+template <typename T, bool CPLX, bool PAL>
 __global__ void __launch_bounds__(256) k_fdtd(const UpdParams p) {
     using A = typename AccT<CPLX>::type;
     using E = Elem<T, CPLX>;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) k_fdtd(const UpdParams p) {
         d[4] = a_scale(sx, a_sub(E::ld(p.halo[0], n), fy));
     } else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
     const unsigned mask = p.nterms ? ((1u << p.nterms) - 1u) : 0u;
-    cell_update<T, CPLX>(p, mask, i, j, k, d);
+    cell_update<T, CPLX, PAL>(p, mask, i, j, k, d);
 }
 
 // Ghost-plane copies F[-1] = F[1]*pp ; F[0] = F[-2]*pm along `axis` for the three
@@ -301,7 +301,7 @@ static int fill_params(ies_ctx* c, int half, UpdParams& p) {
     p.C = c->C[half];
     const bool pal = c->use_palette && c->Cnpal[half] > 0;
     p.Cidx = pal ? c->Cidx[half] : nullptr;
-    p.Cpal = pal ? c->Cpal[half] : nullptr;
+    for (int q = 0; q < MAX_PAL; ++q) p.cpal[q] = pal ? c->Cpal_host[half][q] : 0.0;
     if (!p.C) { set_error("init_update_constants() has not been called (no coefficients uploaded)"); return 1; }
     const bool nb = half == IES_HALF_H ? c->has_next : c->has_prev;
     p.halo[0] = nb ? c->halo_recv[half][0] : nullptr;
@@ -313,7 +313,7 @@ static int fill_params(ies_ctx* c, int half, UpdParams& p) {
     p.i0 = 0; p.i1 = c->cfg.nx;
     p.pstd = c->cfg.method == IES_PSTD;
     p.dz_off = 0;
-    p.pol_dz = c->pol_dz; p.pol_g = c->pol_g;
+    p.prefetch = c->prefetch;
     p.rdx = 1.0 / c->cfg.dx; p.rdy = 1.0 / c->cfg.dy; p.rdz = 1.0 / c->cfg.dz;
     p.nterms = (int)c->terms[half].size();
     for (int t = 0; t < p.nterms; ++t) p.terms[t] = c->terms[half][t];
@@ -327,64 +327,6 @@ static int ensure_scratch(ies_ctx* c, int first, int last) {
     return 0;
 }
 
-// Plan of the fused SHPF half-step (see k_shpf_fused): chunk size cx (a divisor of nx),
-// look-ahead la and the L2-resident scratch ring.
-static int ensure_fused_plan(ies_ctx* c) {
-    FusedPlan& fp = c->fused;
-    if (fp.ready) return 0;
-    const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
-    if (ny != nz || ny < 64 || ny > 512) return 0;
-    int cx = 8, la = 2;
-    if (const char* e = getenv("IES_B200_FUSED_CX")) cx = atoi(e);
-    if (const char* e = getenv("IES_B200_FUSED_LA")) la = atoi(e);
-    if (cx < 1) cx = 1;
-    if (cx > nx) cx = nx;
-    while (nx % cx) --cx;                      // all chunks full
-    if (la < 1) la = 1;
-    const int tt = ny / 16;
-    const int lpb = 256 / tt, w = 256 / tt;
-    fp.cx = cx; fp.la = la; fp.slots = la + 2;
-    fp.nc = nx / cx;
-    fp.kblocks = (nz + w - 1) / w;
-    fp.zitems_full = (cx * ny + lpb - 1) / lpb;
-    fp.total = fp.nc * (fp.zitems_full + cx * fp.kblocks);
-    void* ctr;
-    if (dev_alloc(c, &ctr, sizeof(int) * (size_t)(1 + 2 * fp.nc))) return 1;
-    fp.ctr = (int*)ctr;
-    const size_t rbytes = (size_t)fp.slots * cx * ny * nz * c->esize;
-    void* ring;
-    if (dev_alloc(c, &ring, 2 * rbytes)) return 1;      // one allocation: a single L2 window covers it
-    fp.ring[0] = ring; fp.ring[1] = (char*)ring + rbytes;
-    fp.ready = true;
-    return 0;
-}
-
-// L2 persistence window over the chunk scratch ring (cudaAccessPolicyWindow, both streams).
-static int apply_l2_window(ies_ctx* c) {
-    cudaStreamAttrValue attr;
-    memset(&attr, 0, sizeof(attr));
-    if (c->l2_window && c->chunk_ring) {
-        int max_persist = 0, max_window = 0;
-        IES_CUDA(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->cfg.device));
-        IES_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->cfg.device));
-        const size_t want = c->chunk_ring_bytes;
-        const size_t persist = std::min(want, (size_t)max_persist);
-        IES_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
-        attr.accessPolicyWindow.base_ptr = c->chunk_ring;
-        attr.accessPolicyWindow.num_bytes = std::min(want, (size_t)max_window);
-        attr.accessPolicyWindow.hitRatio = want > 0 ? (float)std::min(1.0, (double)persist / (double)want) : 0.f;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    } else {
-        attr.accessPolicyWindow.num_bytes = 0;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
-    }
-    IES_CUDA(cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
-    IES_CUDA(cudaStreamSetAttribute(c->zstream, cudaStreamAttributeAccessPolicyWindow, &attr));
-    return 0;
-}
-
 // A field component was written in the x-range [lo, hi) outside the update kernels: if the
 // alternating SHPF path's scratch was derived from it, those planes must be refreshed.
 static void mark_field_written(ies_ctx* c, int comp, int lo, int hi) {
@@ -393,83 +335,6 @@ static void mark_field_written(ies_ctx* c, int comp, int lo, int hi) {
     if (!hit || hi <= lo) return;
     if (c->scr_dirty_hi <= c->scr_dirty_lo) { c->scr_dirty_lo = lo; c->scr_dirty_hi = hi; }
     else { c->scr_dirty_lo = std::min(c->scr_dirty_lo, lo); c->scr_dirty_hi = std::max(c->scr_dirty_hi, hi); }
-}
-
-static void drop_graphs(ies_ctx* c) {
-    for (int h = 0; h < 2; ++h) {
-        if (c->graph_exec[h]) { cudaGraphExecDestroy(c->graph_exec[h]); c->graph_exec[h] = nullptr; }
-    }
-}
-
-// x-chunked SHPF half-step: the z derivatives of `chunk` planes live in a small ring
-// (chunk_slots slots) that is rewritten every few chunks and is meant to stay resident in
-// L2 between the kernel that writes a slot and the kernel that reads it.  With two_stream
-// the z-line kernels run on a second stream up to chunk_slots-1 chunks ahead of the y-line
-// kernels, so ramp and tail of one kernel overlap the other; with use_graph the whole
-// launch sequence of a half-step is captured once and replayed.
-template <typename T, bool CP>
-static int chunked_half_step(ies_ctx* c, UpdParams& p, int half) {
-    const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
-    const int ch = c->chunk;
-    const int slots = c->two_stream ? std::max(2, c->chunk_slots) : 1;
-    const int nchunks = (nx + ch - 1) / ch;
-    const size_t cbytes = (size_t)ch * ny * nz * c->esize;
-    const size_t need = 2 * (size_t)slots * cbytes;
-    if (!c->chunk_ring || c->chunk_ring_bytes != need) {
-        IES_CUDA(cudaStreamSynchronize(c->stream));
-        IES_CUDA(cudaStreamSynchronize(c->zstream));
-        if (c->chunk_ring) cudaFree(c->chunk_ring);
-        c->chunk_ring = nullptr;
-        IES_CUDA(cudaMalloc(&c->chunk_ring, need));
-        c->chunk_ring_bytes = need;
-        drop_graphs(c);
-        if (apply_l2_window(c)) return 1;
-    }
-    while ((int)c->ev_z.size() < nchunks) {
-        cudaEvent_t a, b;
-        IES_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-        IES_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-        c->ev_z.push_back(a); c->ev_y.push_back(b);
-    }
-    const bool graph = c->use_graph && !c->profiling;
-    if (graph && c->graph_exec[half]) {
-        IES_CUDA(cudaGraphLaunch(c->graph_exec[half], c->stream));
-        count_launch(2 * nchunks);
-        return 0;
-    }
-    if (graph) IES_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
-    int rc = 0;
-    if (c->two_stream) {
-        cudaEventRecord(c->ev_fork, c->stream);
-        cudaStreamWaitEvent(c->zstream, c->ev_fork, 0);
-    }
-    for (int k = 0; k < nchunks && !rc; ++k) {
-        const int i0 = k * ch, i1 = std::min(nx, i0 + ch), slot = k % slots;
-        void* dA = (char*)c->chunk_ring + (size_t)(2 * slot) * cbytes;
-        void* dB = (char*)c->chunk_ring + (size_t)(2 * slot + 1) * cbytes;
-        cudaStream_t zs = c->two_stream ? c->zstream : c->stream;
-        if (c->two_stream && k >= slots) cudaStreamWaitEvent(zs, c->ev_y[k - slots], 0);
-        rc = launch_zline<T, CP>(c, p.F[1], p.F[0], dA, dB, half, i0, i1, 0, zs);
-        if (rc) break;
-        if (c->two_stream) {
-            cudaEventRecord(c->ev_z[k], zs);
-            cudaStreamWaitEvent(c->stream, c->ev_z[k], 0);
-        }
-        p.dz[0] = dA; p.dz[1] = dB;
-        p.i0 = i0; p.i1 = i1;
-        p.dz_off = -(long long)i0 * ny * nz;
-        rc = launch_yline_update<T, CP>(c, p, half);
-        if (c->two_stream) cudaEventRecord(c->ev_y[k], c->stream);
-    }
-    if (graph) {
-        cudaGraph_t g = nullptr;
-        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
-        if (e != cudaSuccess || rc) { set_error(std::string("graph capture: ") + cudaGetErrorString(e)); if (g) cudaGraphDestroy(g); return 1; }
-        IES_CUDA(cudaGraphInstantiate(&c->graph_exec[half], g, 0));
-        cudaGraphDestroy(g);
-        IES_CUDA(cudaGraphLaunch(c->graph_exec[half], c->stream));
-    }
-    return rc;
 }
 
 template <typename T, bool CP>
@@ -496,7 +361,8 @@ static int do_update(ies_ctx* c, int half) {
         dim3 blk(nz >= 64 ? 64 : 32, nz >= 64 ? 4 : 8, 1);
         dim3 grid((nz + blk.x - 1) / blk.x, (ny + blk.y - 1) / blk.y, nx);
         prof_mark(c, PROF_FDTD, 0);
-        k_fdtd<T, CP><<<grid, blk, 0, c->stream>>>(p);
+        if (p.Cidx) k_fdtd<T, CP, true><<<grid, blk, 0, c->stream>>>(p);
+        else k_fdtd<T, CP, false><<<grid, blk, 0, c->stream>>>(p);
         prof_mark(c, PROF_FDTD, 1);
         count_launch();
         IES_CUDA(cudaGetLastError());
@@ -504,16 +370,6 @@ static int do_update(ies_ctx* c, int half) {
     }
     for (int a = 1; a < 3; ++a)
         if (!c->mult[half][a]) { set_error("spectral multiplier not set (malloc()/init_update_constants() missing)"); return 1; }
-    if (c->cfg.method == IES_SHPF && c->use_fused) {
-        c->scr_kind = SCR_NONE;
-        if (ensure_fused_plan(c)) return 1;
-        const int r = launch_shpf_fused<T, CP>(c, p, half);
-        if (r != 2) return r;
-    }
-    if (c->cfg.method == IES_SHPF && c->chunk > 0 && c->chunk < nx) {
-        c->scr_kind = SCR_NONE;
-        return chunked_half_step<T, CP>(c, p, half);
-    }
     if (ensure_scratch(c, 0, c->cfg.method == IES_PSTD ? 3 : 1)) return 1;
     p.dz[0] = c->scratch[0]; p.dz[1] = c->scratch[1];
     if (c->cfg.method == IES_SHPF && c->use_alt) {
@@ -586,22 +442,12 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     c->use_palette = 1;
     if (const char* e = getenv("IES_B200_PALETTE")) c->use_palette = atoi(e);
     for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
-    // spectral scratch is allocated on first use (full size for the two-kernel path and for
-    // PSTD, a small L2-resident ring for the fused SHPF path)
-    c->use_fused = 0;
-    if (const char* e = getenv("IES_B200_FUSED")) c->use_fused = atoi(e);
-    c->chunk = 0;
-    if (const char* e = getenv("IES_B200_CHUNK")) c->chunk = atoi(e);
-    c->chunk_scratch[0] = c->chunk_scratch[1] = nullptr;
-    c->chunk_ring = nullptr; c->chunk_ring_bytes = 0;
-    c->chunk_slots = 3; c->two_stream = 0; c->use_graph = 0; c->l2_window = 0;
-    c->pol_zin = c->pol_zout = c->pol_dz = c->pol_g = 0;
-    c->graph_exec[0] = c->graph_exec[1] = nullptr;
+    // spectral scratch is allocated on first use
+    c->prefetch = 0;
+    if (const char* e = getenv("IES_B200_PREFETCH")) c->prefetch = atoi(e);
     c->use_alt = 1;
     if (const char* e = getenv("IES_B200_ALT")) c->use_alt = atoi(e);
     c->scr_kind = SCR_NONE; c->scr_dirty_lo = c->scr_dirty_hi = 0;
-    IES_CUDA(cudaStreamCreateWithFlags(&c->zstream, cudaStreamNonBlocking));
-    IES_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     const size_t pbytes = (size_t)cfg->ny * cfg->nz * c->esize;
     for (int h = 0; h < 2; ++h) for (int w = 0; w < 2; ++w) if (dev_alloc(c, &c->halo_recv[h][w], pbytes)) return 1;
     for (int h = 0; h < 2; ++h) for (int a = 0; a < 3; ++a) c->mult[h][a] = nullptr;
@@ -640,14 +486,7 @@ int ies_destroy(ies_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->cfg.device);
     cudaStreamSynchronize(c->stream);
-    cudaStreamSynchronize(c->zstream);
-    drop_graphs(c);
     for (void* p : c->owned) cudaFree(p);
-    if (c->chunk_ring) cudaFree(c->chunk_ring);
-    for (cudaEvent_t e : c->ev_z) cudaEventDestroy(e);
-    for (cudaEvent_t e : c->ev_y) cudaEventDestroy(e);
-    cudaEventDestroy(c->ev_fork);
-    cudaStreamDestroy(c->zstream);
     if (c->stage) cudaFree(c->stage);
     cudaEventDestroy(c->ev_halo);
     cudaStreamDestroy(c->own_stream);
@@ -661,26 +500,20 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     const int v = (int)value;
     IES_CUDA(cudaSetDevice(c->cfg.device));
     IES_CUDA(cudaStreamSynchronize(c->stream));
-    IES_CUDA(cudaStreamSynchronize(c->zstream));
-    drop_graphs(c);
-    if (n == "chunk") c->chunk = v;
-    else if (n == "chunk_slots") c->chunk_slots = v;
-    else if (n == "two_stream") c->two_stream = v;
-    else if (n == "graph") c->use_graph = v;
-    else if (n == "fused") c->use_fused = v;
-    else if (n == "palette") c->use_palette = v;
+    if (n == "palette") c->use_palette = v;
     else if (n == "alt") { c->use_alt = v; c->scr_kind = SCR_NONE; }
-    else if (n == "pol_zin") c->pol_zin = v;
-    else if (n == "pol_zout") c->pol_zout = v;
-    else if (n == "pol_dz") c->pol_dz = v;
-    else if (n == "pol_g") c->pol_g = v;
-    else if (n == "l2_window") { c->l2_window = v; if (apply_l2_window(c)) return 1; }
-    else if (n == "l2_reset") { IES_CUDA(cudaCtxResetPersistingL2Cache()); }
+    else if (n == "prefetch") c->prefetch = v;
+    else if (n == "reset_psi") {               // zero the CPML auxiliary state (restart a run on new fields)
+        for (int h = 0; h < 2; ++h)
+            for (const PmlTermDev& t : c->terms[h])
+                IES_CUDA(cudaMemsetAsync(t.psi, 0, (size_t)t.pdim[0] * t.pdim[1] * t.pdim[2] * c->esize, c->stream));
+        IES_CUDA(cudaStreamSynchronize(c->stream));
+    }
     else { set_error("unknown option " + n); return 1; }
     return 0;
 }
 
-int ies_set_stream(ies_ctx* c, void* s) { drop_graphs(c); c->stream = s ? (cudaStream_t)s : c->own_stream; return 0; }
+int ies_set_stream(ies_ctx* c, void* s) { c->stream = s ? (cudaStream_t)s : c->own_stream; return 0; }
 int ies_timer_start(ies_ctx* c) {
     IES_CUDA(cudaSetDevice(c->cfg.device));
     IES_CUDA(cudaEventRecord(c->ev_t0, c->stream));
@@ -720,7 +553,6 @@ int ies_profile_read(ies_ctx* c, int slot, double* ms_total, int64_t* launches) 
 int ies_sync(ies_ctx* c) { IES_CUDA(cudaSetDevice(c->cfg.device)); IES_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
 
 int ies_set_coeff(ies_ctx* c, int half, const double* host, int64_t n) {
-    drop_graphs(c);
     const size_t ncell = (size_t)c->cfg.nx * c->cfg.ny * c->cfg.nz;
     if (half < 0 || half > 1 || (size_t)n != ncell) { set_error("ies_set_coeff: bad size"); return 1; }
     IES_CUDA(cudaSetDevice(c->cfg.device));
@@ -745,6 +577,8 @@ int ies_set_coeff(ies_ctx* c, int half, const double* host, int64_t n) {
     if ((int)(hp[256] & 0xffffffffu) == 0) {
         int np = 0;
         while (np < 256 && hp[np] != IES_PAL_EMPTY) ++np;
+        if (np > MAX_PAL) return 0;            // too many distinct values: keep the f64 array
+        memcpy(c->Cpal_host[half], hp, sizeof(double) * np);
         k_palette_index<<<1184, 256, 0, c->stream>>>((const unsigned long long*)c->C[half], ncell,
                                                      (const unsigned long long*)c->Cpal[half], c->Cidx[half]);
         count_launch();
@@ -756,14 +590,12 @@ int ies_set_coeff(ies_ctx* c, int half, const double* host, int64_t n) {
 }
 
 int ies_set_update_box(ies_ctx* c, int comp, const int32_t lo[3], const int32_t hi[3]) {
-    drop_graphs(c);
     if (comp < 0 || comp > 5) { set_error("bad component"); return 1; }
     for (int a = 0; a < 3; ++a) { c->ubox[comp].lo[a] = lo[a]; c->ubox[comp].hi[a] = hi[a]; }
     return 0;
 }
 
 int ies_set_multiplier(ies_ctx* c, int half, int axis, const double* re_im, int32_t n) {
-    drop_graphs(c);
     c->scr_kind = SCR_NONE;
     const int dims[3] = {c->cfg.nx, c->cfg.ny, c->cfg.nz};
     if (half < 0 || half > 1 || axis < 0 || axis > 2 || n != dims[axis]) { set_error("ies_set_multiplier: bad args"); return 1; }
@@ -780,10 +612,9 @@ int ies_set_multiplier(ies_ctx* c, int half, int axis, const double* re_im, int3
     return 0;
 }
 
-int ies_clear_pml(ies_ctx* c) { drop_graphs(c); c->terms[0].clear(); c->terms[1].clear(); return 0; }
+int ies_clear_pml(ies_ctx* c) { c->terms[0].clear(); c->terms[1].clear(); return 0; }
 
 int ies_add_pml_term(ies_ctx* c, const ies_pml_term* t) {
-    drop_graphs(c);
     if (!t || t->half < 0 || t->half > 1 || t->comp < 0 || t->comp > 2 || t->diff < 0 || t->diff > 5 || t->axis < 0 || t->axis > 2) {
         set_error("ies_add_pml_term: bad term"); return 1;
     }
@@ -825,7 +656,7 @@ int ies_set_ghost(ies_ctx* c, int axis, int enabled, double ppr, double ppi, dou
     return 0;
 }
 
-int ies_set_neighbours(ies_ctx* c, int has_prev, int has_next) { drop_graphs(c); c->has_prev = has_prev; c->has_next = has_next; return 0; }
+int ies_set_neighbours(ies_ctx* c, int has_prev, int has_next) { c->has_prev = has_prev; c->has_next = has_next; return 0; }
 
 int ies_update_h(ies_ctx* c, int64_t) {
     IES_CUDA(cudaSetDevice(c->cfg.device));
@@ -884,6 +715,7 @@ int ies_put_src(ies_ctx* c, int comp, const int32_t lo[3], const int32_t hi[3], 
     const long n = (long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
     if (n <= 0) return 0;
     IES_CUDA(cudaSetDevice(c->cfg.device));
+    mark_field_written(c, comp, lo[0], hi[0]);
     double2 *dpx = nullptr, *dpy = nullptr, *dpz = nullptr;
     void* tmp = nullptr;
     if (px && py && pz) {

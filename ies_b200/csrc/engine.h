@@ -10,6 +10,7 @@
 
 namespace ies {
 
+constexpr int MAX_PAL = 32;     // palette entries carried in the kernel parameters
 constexpr int MAX_TERMS = 12;   // 6 faces x 2 components per half-step (space.py:1054-1108)
 
 struct Box { int lo[3], hi[3]; };
@@ -29,8 +30,9 @@ struct UpdParams {
     const void* F[3];           // differentiated field (E in updateH, H in updateE): x,y,z
     void* G[3];                 // updated field
     const double* C;            // CH2 / CE2 (space.py:445-553, zero conductivity)
-    const uint8_t* Cidx;        // lossless palette form of C (<= 256 distinct values) or null:
-    const double* Cpal;         //   C[i] == Cpal[Cidx[i]] bit for bit; 1 B/cell of HBM traffic instead of 8
+    const uint8_t* Cidx;        // lossless palette form of C (<= MAX_PAL distinct values) or null:
+    double cpal[MAX_PAL];       //   C[i] == cpal[Cidx[i]] bit for bit; 1 B/cell of HBM traffic instead of 8,
+                                //   the palette itself sits in the kernel-parameter constant bank
     const void* halo[2];        // neighbour planes of F_y, F_z (or null)
     const void* dz[2];          // scratch: d/dz F_y, d/dz F_x   (spectral methods)
     const void* dxs[2];         // scratch: d/dx F_z, d/dx F_y   (PSTD)
@@ -39,20 +41,11 @@ struct UpdParams {
     int i0, i1;                 // x range handled by this launch
     int pstd;                   // x derivative comes from dxs[]
     long long dz_off;           // element offset of the dz scratch relative to the field index
-    int pol_dz, pol_g;          // L2 eviction policy (mem_hint.cuh POL_*) of the scratch reads / G traffic
+    int prefetch;               // 1: CTAs prefetch their streaming operands into L2 at start
     double rdx, rdy, rdz;
     Box box[3];
     int nterms;
     PmlTermDev terms[MAX_TERMS];
-};
-
-// Work plan of the fused persistent SHPF half-step (spectral.cuh: k_shpf_fused).
-struct FusedPlan {
-    bool ready = false;
-    int cx = 0, la = 0, slots = 0, nc = 0, kblocks = 0, zitems_full = 0, nsegs = 0, total = 0;
-    int* ctr = nullptr;        // 1 + 2*nc counters (device)
-    void* ring[2] = {nullptr, nullptr};   // z-derivative scratch ring: slots*cx planes each
-    int grid[2] = {0, 0};
 };
 
 struct Ctx {
@@ -63,7 +56,8 @@ struct Ctx {
     void* F[6];
     double* C[2];
     uint8_t* Cidx[2];           // palette-compressed coefficients (valid when Cnpal > 0)
-    double* Cpal[2];
+    double* Cpal[2];            // device scratch of the palette builder (256 slots + overflow flag)
+    double Cpal_host[2][MAX_PAL];
     int Cnpal[2];
     int use_palette;
     void* scratch[4];           // dzA dzB dxA dxB
@@ -81,25 +75,12 @@ struct Ctx {
     cudaEvent_t ev_t0, ev_t1;          // ies_timer_start/stop
     int profiling;                     // per-kernel CUDA-event timing on/off
     std::vector<cudaEvent_t> prof_ev[4][2];   // [slot][begin/end]
-    FusedPlan fused;
-    int use_fused;                     // 1: fused persistent SHPF half-step when applicable
-    int chunk;                         // x planes per (z-line, y-line) launch pair; 0 = whole slab
-    void* chunk_scratch[2];
-    int chunk_slots;                   // ring slots of the chunk scratch (two-stream pipeline)
-    int two_stream;                    // z-line kernels on a second stream, one chunk ahead
-    cudaStream_t zstream;
-    std::vector<cudaEvent_t> ev_z, ev_y;
-    cudaEvent_t ev_fork;
-    int pol_zin, pol_zout, pol_dz, pol_g;   // L2 eviction policies (mem_hint.cuh)
-    int l2_window;                     // cudaAccessPolicyWindow (persisting) on the chunk scratch
-    void* chunk_ring; size_t chunk_ring_bytes;
+    int prefetch;                      // UpdParams::prefetch
     // alternating-orientation SHPF path (shpf_half.cuh): what the scratch pair currently holds
     // and the x-range in which it is stale (fields written since it was produced)
     int use_alt;
     int scr_kind;                      // SCR_NONE / SCR_FOR_H (d/dy of E_z,E_x) / SCR_FOR_E (d/dz of H_y,H_x)
     int scr_dirty_lo, scr_dirty_hi;
-    int use_graph;                     // replay the chunked half-step as a CUDA graph
-    cudaGraphExec_t graph_exec[2];
 };
 
 enum { SCR_NONE = 0, SCR_FOR_H = 1, SCR_FOR_E = 2 };
@@ -122,8 +103,6 @@ template <typename T, bool CPLX>
 int launch_shpf_half(Ctx* c, const UpdParams& p, int half);
 template <typename T, bool CPLX>
 int launch_yline_update(Ctx* c, const UpdParams& p, int half);
-template <typename T, bool CPLX>
-int launch_shpf_fused(Ctx* c, const UpdParams& p, int half);
 
 bool fft_len_supported(int n);
 

@@ -26,7 +26,7 @@ namespace ies {
 
 enum { ORI_Y = 0, ORI_Z = 1 };
 
-template <typename T, bool CPLX, int N, int ORI>
+template <typename T, bool CPLX, int N, int ORI, bool PAL>
 __global__ void __launch_bounds__(256, (CPLX ? 1 : 2))
 k_shpf_half(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
             const typename Cx<T>::type* __restrict__ ml_in, const typename Cx<T>::type* __restrict__ ml_out) {
@@ -65,6 +65,30 @@ k_shpf_half(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
         if (ORI == ORI_Y) return r * NL + cc;
         return r * N + XchgContigSw<C, N>::phys(cc);
     };
+
+    const int in = i + p.dir;                    // x neighbour plane
+    const bool nb_inside = (in >= 0 && in < p.nx);
+    const bool nb_any = nb_inside || p.halo[0] != nullptr;
+    const void* nFy = nb_inside ? p.F[1] : p.halo[0];
+    const void* nFz = nb_inside ? p.F[2] : p.halo[1];
+    const size_t nbase = nb_inside ? (size_t)in * plane : 0;
+    if (p.prefetch) {
+        // operands of phase B travel HBM -> L2 while phase A computes
+        constexpr int ES = (int)sizeof(T) * (CPLX ? 2 : 1);
+        const int rows = min(ROWS, p.ny - j0), cols = min(COLS, p.nz - k0);
+        const size_t fb = ((size_t)i * plane + (size_t)j0 * p.nz + k0) * ES, rs = (size_t)p.nz * ES;
+        const size_t nb = (nbase + (size_t)j0 * p.nz + k0) * ES;
+        prefetch_rows_l2(p.dz[0], fb, rows, cols * ES, rs);
+        prefetch_rows_l2(p.dz[1], fb, rows, cols * ES, rs);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) prefetch_rows_l2(p.G[c], fb, rows, cols * ES, rs);
+        if (nb_any) {
+            prefetch_rows_l2(ORI == ORI_Y ? p.F[1] : p.F[2], fb, rows, cols * ES, rs);
+            prefetch_rows_l2(nFy, nb, rows, cols * ES, rs);
+            prefetch_rows_l2(nFz, nb, rows, cols * ES, rs);
+        }
+        if (!PAL) prefetch_rows_l2(p.C, ((size_t)i * plane + (size_t)j0 * p.nz + k0) * 8, rows, cols * 8, (size_t)p.nz * 8);
+    }
 
     // ---------------- phase A: derivative of the F pair along the tile's line axis ----------------
     // ORI_Y: pair (F_z, F_x) -> d/dy F_z (slot 0), d/dy F_x (slot 5)
@@ -108,12 +132,6 @@ k_shpf_half(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
         constexpr int PB = (NIT % 2 == 0) ? 2 : 1;   // iterations whose loads are batched
         const unsigned mask = ORI == ORI_Y ? term_mask(p, i, i + 1, 0, p.ny, k0, k0 + NL)
                                            : term_mask(p, i, i + 1, j0, j0 + NL, 0, p.nz);
-        const int in = i + p.dir;                    // x neighbour plane
-        const bool nb_inside = (in >= 0 && in < p.nx);
-        const bool nb_any = nb_inside || p.halo[0] != nullptr;
-        const void* nFy = nb_inside ? p.F[1] : p.halo[0];
-        const void* nFz = nb_inside ? p.F[2] : p.halo[1];
-        const size_t nbase = nb_inside ? (size_t)in * plane : 0;
         const double sx = p.dir > 0 ? p.rdx : -p.rdx;
 #pragma unroll 1
         for (int it0 = 0; it0 < NIT; it0 += PB) {
@@ -139,7 +157,7 @@ k_shpf_half(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
                 }
 #pragma unroll
                 for (int c = 0; c < 3; ++c) VV::ld(p.G[c], idx, g[u][c]);
-                ld_coeff<V>(p, idx, cf[u]);
+                ld_coeff<V, PAL>(p, idx, cf[u]);
             }
 #pragma unroll
             for (int u = 0; u < PB; ++u) {
@@ -233,23 +251,23 @@ int launch_shpf_half(Ctx* c, const UpdParams& p, int half) {
     const C* ml_in = (const C*)c->mult[half][axis];
     const C* ml_out = (const C*)c->mult[half ^ 1][axis];
     const size_t sm = sizeof(C) * 4096 * Fld<T, CPLX>::NF;
+    const bool pal = p.Cidx != nullptr;
+#define H_LAUNCH(NN, OO, PP) {                                                              \
+        auto kern = k_shpf_half<T, CPLX, NN, OO, PP>;                                       \
+        if (set_smem(kern, sm)) return 1;                                                   \
+        kern<<<grid, 256, sm, c->stream>>>(p, tw, ml_in, ml_out);                           \
+    }
 #define H_CASE(NN) {                                                                        \
         constexpr int NL = 256 / (NN / 16);                                                 \
         dim3 grid((unsigned)((other + NL - 1) / NL), (unsigned)(p.i1 - p.i0));              \
-        if (ori == ORI_Y) {                                                                 \
-            auto kern = k_shpf_half<T, CPLX, NN, ORI_Y>;                                    \
-            if (set_smem(kern, sm)) return 1;                                               \
-            kern<<<grid, 256, sm, c->stream>>>(p, tw, ml_in, ml_out);                       \
-        } else {                                                                            \
-            auto kern = k_shpf_half<T, CPLX, NN, ORI_Z>;                                    \
-            if (set_smem(kern, sm)) return 1;                                               \
-            kern<<<grid, 256, sm, c->stream>>>(p, tw, ml_in, ml_out);                       \
-        }                                                                                   \
+        if (ori == ORI_Y) { if (pal) H_LAUNCH(NN, ORI_Y, true) else H_LAUNCH(NN, ORI_Y, false) } \
+        else              { if (pal) H_LAUNCH(NN, ORI_Z, true) else H_LAUNCH(NN, ORI_Z, false) } \
     }
     prof_mark(c, PROF_YLINE_UPDATE, 0);
     IES_FOR_N(n, H_CASE)
     prof_mark(c, PROF_YLINE_UPDATE, 1);
 #undef H_CASE
+#undef H_LAUNCH
     count_launch();
     IES_CUDA(cudaGetLastError());
     return 0;

@@ -29,12 +29,6 @@ template <typename T> struct Fld<T, false> {
     static __device__ __forceinline__ void st(void* dA, void* dB, size_t i, C v, int) {
         ((T*)dA)[i] = v.x; ((T*)dB)[i] = v.y;
     }
-    template <bool HINT> static __device__ __forceinline__ C ldp(const void* A, const void* B, size_t i, int, uint64_t pol) {
-        C v; v.x = ld_pol<HINT>((const T*)A + i, pol); v.y = ld_pol<HINT>((const T*)B + i, pol); return v;
-    }
-    template <bool HINT> static __device__ __forceinline__ void stp(void* dA, void* dB, size_t i, C v, int, uint64_t pol) {
-        st_pol<HINT>((T*)dA + i, v.x, pol); st_pol<HINT>((T*)dB + i, v.y, pol);
-    }
 };
 template <typename T> struct Fld<T, true> {
     using C = typename Cx<T>::type;
@@ -44,12 +38,6 @@ template <typename T> struct Fld<T, true> {
     }
     static __device__ __forceinline__ void st(void* dA, void* dB, size_t i, C v, int f) {
         ((C*)(f == 0 ? dA : dB))[i] = v;
-    }
-    template <bool HINT> static __device__ __forceinline__ C ldp(const void* A, const void* B, size_t i, int f, uint64_t pol) {
-        return ld_pol<HINT>((const C*)(f == 0 ? A : B) + i, pol);
-    }
-    template <bool HINT> static __device__ __forceinline__ void stp(void* dA, void* dB, size_t i, C v, int f, uint64_t pol) {
-        st_pol<HINT>((C*)(f == 0 ? dA : dB) + i, v, pol);
     }
 };
 
@@ -66,77 +54,44 @@ template <int N> struct ZCfg {
     static constexpr int THREADS = LPB * TT;
 };
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-    int v; asm volatile("ld.global.acquire.gpu.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ void red_release(int* p) {
-    asm volatile("red.global.release.gpu.add.s32 [%0], 1;" :: "l"(p) : "memory");
-}
-// thread 0 spins until *ctr >= need (no-op when ctr is null); callers follow with a CTA barrier
-__device__ __forceinline__ void wait_counter(const int* ctr, int need) {
-    if (need > 0 && threadIdx.x == 0) {
-        while (ld_acquire(ctr) < need) __nanosleep(32);
-    }
-}
-
-// One work item = LPB adjacent z lines.  Input lines start at in_line0 (+ item*LPB), the
-// derivative lines go to out_line0 (+ item*LPB) of the scratch arrays.
-template <typename T, bool CPLX, int N, bool HINT = false>
-__device__ __forceinline__ void zline_item(const void* __restrict__ A, const void* __restrict__ B,
-                                           void* __restrict__ dA, void* __restrict__ dB,
-                                           long in_line0, long out_line0, long nlines, long item,
-                                           const typename Cx<T>::type* tw, const typename Cx<T>::type* ml,
-                                           typename Cx<T>::type* xbuf,
-                                           const int* dep_ctr = nullptr, int dep_need = 0,
-                                           uint64_t pin = 0, uint64_t pout = 0) {
+// One CTA = LPB adjacent z lines.  Input lines start at line0 (+ blockIdx.x*LPB), the
+// derivative lines go to oline0 (+ blockIdx.x*LPB) of the scratch arrays.
+template <typename T, bool CPLX, int N>
+__global__ void __launch_bounds__(ZCfg<N>::THREADS)
+k_zline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict__ dA,
+        void* __restrict__ dB, long line0, long oline0, long nlines,
+        const typename Cx<T>::type* __restrict__ twg, const typename Cx<T>::type* __restrict__ mlg) {
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* tw = reinterpret_cast<C*>(smem_raw);
+    C* ml = tw + N;
+    C* xbuf = ml + N;
+    load_tables(tw, ml, twg, mlg, N);
     constexpr int TT = ZCfg<N>::TT, LPB = ZCfg<N>::LPB;
     const int t = threadIdx.x % TT, l = threadIdx.x / TT;
-    const long line = item * LPB + l;
+    const long line = (long)blockIdx.x * LPB + l;
     const bool ok = line < nlines;
-    const size_t ibase = (size_t)(in_line0 + line) * N;
-    const size_t obase = (size_t)(out_line0 + line) * N;
+    const size_t ibase = (size_t)(line0 + line) * N;
+    const size_t obase = (size_t)(oline0 + line) * N;
     XchgContig<C, N> xb{xbuf + (size_t)l * XchgContig<C, N>::LS};
 #pragma unroll 1
     for (int f = 0; f < F::NF; ++f) {
         C v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            if (ok) v[q] = F::template ldp<HINT>(A, B, ibase + line_index<N>(t, q), f, pin);
+            if (ok) v[q] = F::ld(A, B, ibase + line_index<N>(t, q), f);
             else { v[q].x = 0; v[q].y = 0; }
         }
         fft_forward<N>(v, t, tw, xb);
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], ml[spec_index<N>(t, q)]);
         fft_inverse<N>(v, t, tw, xb);
-        if (dep_need > 0 && f == 0) {            // output slot free? (fused kernel only; CTA-uniform)
-            wait_counter(dep_ctr, dep_need);
-            __syncthreads();
-        }
         if (ok) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) F::template stp<HINT>(dA, dB, obase + line_index<N>(t, q), v[q], f, pout);
+            for (int q = 0; q < 16; ++q) F::st(dA, dB, obase + line_index<N>(t, q), v[q], f);
         }
     }
-}
-
-template <typename T, bool CPLX, int N, bool HINT>
-__global__ void __launch_bounds__(ZCfg<N>::THREADS)
-k_zline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict__ dA,
-        void* __restrict__ dB, long line0, long oline0, long nlines,
-        const typename Cx<T>::type* __restrict__ twg, const typename Cx<T>::type* __restrict__ mlg,
-        const int pol_in, const int pol_out) {
-    using C = typename Cx<T>::type;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C* tw = reinterpret_cast<C*>(smem_raw);
-    C* ml = tw + N;
-    C* xbuf = ml + N;
-    load_tables(tw, ml, twg, mlg, N);
-    uint64_t pin = 0, pout = 0;
-    if constexpr (HINT) { pin = make_policy(pol_in); pout = make_policy(pol_out); }
-    zline_item<T, CPLX, N, HINT>(A, B, dA, dB, line0, oline0, nlines, (long)blockIdx.x, tw, ml, xbuf,
-                                 nullptr, 0, pin, pout);
 }
 
 // ------------------------------------------------------- strided lines (x) -----
@@ -186,21 +141,33 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 }
 
 // ------------------------------------------ y lines + fused field update -----
+// L2 prefetch of a tile's rows (row_bytes each, rows row_stride bytes apart): one
+// prefetch.global.L2 per 128-byte line, spread over the CTA.  Fire-and-forget: the tile's
+// later loads find their lines in L2 instead of paying the HBM latency inside the batch.
+__device__ __forceinline__ void prefetch_rows_l2(const void* base, size_t first_byte, int rows,
+                                                 int row_bytes, size_t row_stride) {
+    if (base == nullptr) return;
+    const int lpr = (row_bytes + 127) / 128;
+    const int total = rows * lpr;
+    for (int l = threadIdx.x; l < total; l += blockDim.x) {
+        const int r = l / lpr, c = l - r * lpr;
+        const char* a = (const char*)base + first_byte + (size_t)r * row_stride + (size_t)c * 128;
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
+    }
+}
+
 // Phase A: W adjacent y lines (one per column, lane = column) are transformed in
 //          registers; the derivative pair lands in shared memory in tile layout
 //          stash[row * W + col].
 // Phase B: the CTA re-maps to 16-byte vectors along z (V cells per thread) and streams
 //          the cell update: PB row groups of loads are issued before any arithmetic so
 //          enough bytes are in flight to cover HBM latency.
-// One work item = the tile (plane i, columns kb*W .. kb*W+W-1, all rows).  dz_off is the
-// element offset added to a cell index when reading the z-derivative scratch (0 for
-// full-size scratch, ring-slot offset in the fused kernel); DZCG selects ld.global.cg
-// for those reads (data produced by other CTAs of the same launch).
-template <typename T, bool CPLX, int N, bool DZCG, bool HINT = false>
-__device__ __forceinline__ void yline_item(const UpdParams& p, const int i, const int kb, const long long dz_off,
-                                           const typename Cx<T>::type* tw, const typename Cx<T>::type* ml,
-                                           typename Cx<T>::type* xbuf,
-                                           const int* dep_ctr = nullptr, int dep_need = 0) {
+// One CTA = the tile (plane i, columns kb*W .. kb*W+W-1, all rows).  PAL: coefficients come
+// from the palette form (update_dev.cuh ld_coeff).
+template <typename T, bool CPLX, int N, bool PAL>
+__global__ void __launch_bounds__(256, (CPLX ? 1 : 2))
+k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
+               const typename Cx<T>::type* __restrict__ ml) {
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
     using A = typename AccT<CPLX>::type;
@@ -209,8 +176,39 @@ __device__ __forceinline__ void yline_item(const UpdParams& p, const int i, cons
     constexpr int W = S::W;
     constexpr int V = VV::V;
     constexpr int NF = F::NF;
-    const int k0 = kb * W;
+    // The twiddle / multiplier tables are read straight from global memory (L1-resident,
+    // 8 KB): that keeps the CTA at N*W*16 B of shared memory, so two CTAs fit the 132 KB
+    // carve-out and 96 KB of L1 remain for loads in flight (measured: the kernel's
+    // bandwidth follows the L1 size left by the carve-out).
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* xbuf = reinterpret_cast<C*>(smem_raw);      // NF buffers of N*W: exchange, then derivative stash
+    const int i = p.i0 + (int)blockIdx.y;
+    const int k0 = (int)blockIdx.x * W;
     const size_t plane = (size_t)p.ny * p.nz;
+    const int in = i + p.dir;                       // x neighbour plane
+    const bool nb_inside = (in >= 0 && in < p.nx);
+    const bool nb_any = nb_inside || p.halo[0] != nullptr;
+    const void* nFy = nb_inside ? p.F[1] : p.halo[0];
+    const void* nFz = nb_inside ? p.F[2] : p.halo[1];
+    const size_t nbase = nb_inside ? (size_t)in * plane : 0;
+    if (p.prefetch) {
+        constexpr int ES = S::ES;
+        const size_t fb = ((size_t)i * plane + k0) * ES, rs = (size_t)p.nz * ES;
+        const int cols = min(W, p.nz - k0);
+        prefetch_rows_l2(p.dz[0], (size_t)((long long)fb + p.dz_off * ES), N, cols * ES, rs);
+        prefetch_rows_l2(p.dz[1], (size_t)((long long)fb + p.dz_off * ES), N, cols * ES, rs);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) prefetch_rows_l2(p.G[c], fb, N, cols * ES, rs);
+        if (p.pstd) {
+            prefetch_rows_l2(p.dxs[0], fb, N, cols * ES, rs);
+            prefetch_rows_l2(p.dxs[1], fb, N, cols * ES, rs);
+        } else if (nb_any) {
+            prefetch_rows_l2(p.F[1], fb, N, cols * ES, rs);
+            prefetch_rows_l2(nFy, (nbase + k0) * ES, N, cols * ES, rs);
+            prefetch_rows_l2(nFz, (nbase + k0) * ES, N, cols * ES, rs);
+        }
+        if (!PAL) prefetch_rows_l2(p.C, ((size_t)i * plane + k0) * 8, N, cols * 8, (size_t)p.nz * 8);
+    }
     {
         const int c = threadIdx.x % W, t = threadIdx.x / W;
         const int k = k0 + c;
@@ -234,7 +232,6 @@ __device__ __forceinline__ void yline_item(const UpdParams& p, const int i, cons
 #pragma unroll
             for (int q = 0; q < 16; ++q) xb.st(line_index<N>(t, q), v[q]);
         }
-        wait_counter(dep_ctr, dep_need);     // z derivatives of this chunk produced? (fused kernel only)
         __syncthreads();
     }
     // ---------------- phase B: vectorised streaming update ----------------
@@ -246,15 +243,7 @@ __device__ __forceinline__ void yline_item(const UpdParams& p, const int i, cons
     const int k = k0 + cg * V;
     if (k >= p.nz) return;
     const unsigned mask = term_mask(p, i, i + 1, 0, p.ny, k0, k0 + W);
-    const int in = i + p.dir;                       // x neighbour plane
-    const bool nb_inside = (in >= 0 && in < p.nx);
-    const bool nb_any = nb_inside || p.halo[0] != nullptr;
-    const void* nFy = nb_inside ? p.F[1] : p.halo[0];
-    const void* nFz = nb_inside ? p.F[2] : p.halo[1];
-    const size_t nbase = nb_inside ? (size_t)in * plane : 0;
     const double sx = p.dir > 0 ? p.rdx : -p.rdx;
-    uint64_t pdz = 0, pg = 0;
-    if constexpr (HINT) { pdz = make_policy(p.pol_dz); pg = make_policy(p.pol_g); }
 #pragma unroll 1
     for (int pass0 = 0; pass0 < NPASS; pass0 += PB) {
         A dz0[PB][V], dz1[PB][V], a3[PB][V], a4[PB][V], b3[PB][V], b4[PB][V], g[PB][3][V];
@@ -263,13 +252,8 @@ __device__ __forceinline__ void yline_item(const UpdParams& p, const int i, cons
         for (int u = 0; u < PB; ++u) {
             const int j = tr + (pass0 + u) * RP;
             const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
-            if constexpr (DZCG) {
-                VV::template ldx<true>(p.dz[0], (size_t)((long long)idx + dz_off), dz0[u]);
-                VV::template ldx<true>(p.dz[1], (size_t)((long long)idx + dz_off), dz1[u]);
-            } else {
-                VV::template ldp<HINT>(p.dz[0], (size_t)((long long)idx + dz_off), dz0[u], pdz);
-                VV::template ldp<HINT>(p.dz[1], (size_t)((long long)idx + dz_off), dz1[u], pdz);
-            }
+            VV::ld(p.dz[0], (size_t)((long long)idx + p.dz_off), dz0[u]);
+            VV::ld(p.dz[1], (size_t)((long long)idx + p.dz_off), dz1[u]);
             if (p.pstd) {
                 VV::ld(p.dxs[0], idx, a3[u]);
                 VV::ld(p.dxs[1], idx, a4[u]);
@@ -281,8 +265,8 @@ __device__ __forceinline__ void yline_item(const UpdParams& p, const int i, cons
                 VV::ld(p.F[1], idx, b4[u]);
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) VV::template ldp<HINT>(p.G[c], idx, g[u][c], pg);
-            ld_coeff<V>(p, idx, cf[u]);
+            for (int c = 0; c < 3; ++c) VV::ld(p.G[c], idx, g[u][c]);
+            ld_coeff<V, PAL>(p, idx, cf[u]);
         }
 #pragma unroll
         for (int u = 0; u < PB; ++u) {
@@ -311,115 +295,7 @@ __device__ __forceinline__ void yline_item(const UpdParams& p, const int i, cons
                 g[u][0][v] = gg[0]; g[u][1][v] = gg[1]; g[u][2][v] = gg[2];
             }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) VV::template stp<HINT>(p.G[c], idx, g[u][c], pg);
-        }
-    }
-}
-
-template <typename T, bool CPLX, int N, bool HINT>
-__global__ void __launch_bounds__(256, (CPLX ? 1 : 2))
-k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ twg,
-               const typename Cx<T>::type* __restrict__ mlg, const int tables_in_smem) {
-    using C = typename Cx<T>::type;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    // The twiddle / multiplier tables are read straight from global memory (L1-resident,
-    // 8 KB) by default: that keeps the CTA at N*W*16 B of shared memory, so two CTAs fit the
-    // 132 KB carve-out and 96 KB of L1 remain for loads in flight (measured: the kernel's
-    // bandwidth follows the L1 size left by the carve-out).
-    const C* tw = twg;
-    const C* ml = mlg;
-    C* xbuf = reinterpret_cast<C*>(smem_raw);      // NF buffers of N*W: exchange, then derivative stash
-    if (tables_in_smem) {
-        C* stw = reinterpret_cast<C*>(smem_raw);
-        C* sml = stw + N;
-        xbuf = sml + N;
-        load_tables(stw, sml, twg, mlg, N);
-        tw = stw; ml = sml;
-    }
-    yline_item<T, CPLX, N, false, HINT>(p, p.i0 + (int)blockIdx.y, (int)blockIdx.x, p.dz_off, tw, ml, xbuf);
-}
-
-// ------------------------------------------------ fused persistent half-step -----
-// SHPF half-step as ONE persistent launch: z-line items and y-line/update items are
-// pulled from a global queue ordered so that a chunk's z derivatives are produced two
-// groups before they are consumed; the scratch is a 3-chunk ring that stays resident in
-// the 126 MB L2, so the z derivatives never travel to HBM.  Dependencies are per-chunk
-// completion counters (release/acquire at gpu scope); an item is only claimed by a
-// running CTA and never waits on an item claimed later, so the scheme cannot deadlock.
-struct FusedArgs {
-    int total;
-    int* ctr;            // [0] queue head, [1 .. nc] z items done, [1+nc .. 2nc] y items done
-    int nc, cx, la;      // chunks, planes per chunk, look-ahead of the z items (chunks)
-    int slots;           // ring slots of the z-derivative scratch
-    int kblocks;         // y-line items per plane
-    int zitems_full;     // z items of a full chunk (cx*ny/LPB)
-    int debug_skip;      // development: 1 = skip y work, 2 = skip z work
-};
-
-
-template <typename T, bool CPLX, int N>
-__global__ void __launch_bounds__(256, (CPLX ? 1 : 2))
-k_shpf_fused(const UpdParams p, const FusedArgs fa,
-             const typename Cx<T>::type* __restrict__ twz, const typename Cx<T>::type* __restrict__ mlz,
-             const typename Cx<T>::type* __restrict__ twy, const typename Cx<T>::type* __restrict__ mly) {
-    using C = typename Cx<T>::type;
-    static_assert(ZCfg<N>::THREADS == 256 && SCfg<T, CPLX, N>::THREADS == 256, "fused kernel needs 256-thread items");
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C* tz = reinterpret_cast<C*>(smem_raw);
-    C* mz = tz + N;
-    C* ty = mz + N;
-    C* my = ty + N;
-    C* xbuf = my + N;
-    for (int q = threadIdx.x; q < N; q += blockDim.x) { tz[q] = twz[q]; mz[q] = mlz[q]; ty[q] = twy[q]; my[q] = mly[q]; }
-    __shared__ int s_item[2];
-    const size_t plane = (size_t)p.ny * p.nz;
-    // queue layout (all chunks are full: cx divides nx):
-    //   [z(0) .. z(la-1)] then for c = 0 .. nc-1: y(c), z(c+la) (z only while c+la < nc)
-    const int zf = fa.zitems_full, yf = fa.cx * fa.kblocks;
-    const int head = min(fa.la, fa.nc) * zf;
-    const int npair = max(fa.nc - fa.la, 0);            // chunks c that are followed by z(c+la)
-    if (threadIdx.x == 0) s_item[0] = atomicAdd(&fa.ctr[0], 1);
-    int par = 0;
-    while (true) {
-        __syncthreads();                       // s_item[par] visible; previous item done with smem
-        const int item = s_item[par];
-        if (item >= fa.total) break;
-        if (threadIdx.x == 0) s_item[par ^ 1] = atomicAdd(&fa.ctr[0], 1);   // prefetch the next claim
-        par ^= 1;
-        int type, c, local;
-        if (item < head) { type = 0; c = item / zf; local = item - c * zf; }
-        else {
-            const int r = item - head;
-            const int pairs_items = npair * (yf + zf);
-            if (r < pairs_items) {
-                const int pr = r / (yf + zf), w = r - pr * (yf + zf);
-                if (w < yf) { type = 1; c = pr; local = w; }
-                else { type = 0; c = pr + fa.la; local = w - yf; }
-            } else {
-                const int r2 = r - pairs_items;
-                type = 1; c = npair + r2 / yf; local = r2 - (r2 / yf) * yf;
-            }
-        }
-        const int pl0 = c * fa.cx;                                   // first plane of the chunk
-        const int slot = c % fa.slots;
-        if (type == 0) {
-            // the ring slot must have been consumed by the y items of chunk c-slots
-            if (fa.debug_skip == 2) { if (threadIdx.x == 0) red_release(&fa.ctr[1 + c]); continue; }
-            const bool wrap = c >= fa.slots;
-            const int* dep = &fa.ctr[wrap ? 1 + fa.nc + (c - fa.slots) : 0];
-            zline_item<T, CPLX, N>(p.F[1], p.F[0], const_cast<void*>(p.dz[0]), const_cast<void*>(p.dz[1]),
-                                   (long)pl0 * p.ny, (long)slot * fa.cx * p.ny, (long)fa.cx * p.ny, (long)local,
-                                   tz, mz, xbuf, dep, wrap ? yf : 0);
-            __syncthreads();
-            if (threadIdx.x == 0) { __threadfence(); red_release(&fa.ctr[1 + c]); }
-        } else {
-            if (fa.debug_skip == 1) { if (threadIdx.x == 0) red_release(&fa.ctr[1 + fa.nc + c]); continue; }
-            const int i = pl0 + local / fa.kblocks;
-            const int kb = local - (local / fa.kblocks) * fa.kblocks;
-            const long long dz_off = ((long long)slot * fa.cx - pl0) * (long long)plane;
-            yline_item<T, CPLX, N, true>(p, i, kb, dz_off, ty, my, xbuf, &fa.ctr[1 + c], zf);
-            __syncthreads();
-            if (threadIdx.x == 0) { __threadfence(); red_release(&fa.ctr[1 + fa.nc + c]); }
+            for (int c = 0; c < 3; ++c) VV::st(p.G[c], idx, g[u][c]);
         }
     }
 }
@@ -448,7 +324,6 @@ int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
                  cudaStream_t st) {
     using C = typename Cx<T>::type;
     if (!st) st = c->stream;
-    const bool hint = (c->pol_zin | c->pol_zout) != 0;
     const int n = c->cfg.nz;
     const long nlines = (long)(i1 - i0) * c->cfg.ny;
     const long line0 = (long)i0 * c->cfg.ny;
@@ -457,11 +332,11 @@ int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
 #define Z_CASE(NN) {                                                                        \
         constexpr int LPB = ZCfg<NN>::LPB;                                                  \
         size_t sm = sizeof(C) * (2 * NN + (size_t)LPB * XchgContig<C, NN>::LS);             \
-        auto kern = hint ? k_zline<T, CPLX, NN, true> : k_zline<T, CPLX, NN, false>;        \
+        auto kern = k_zline<T, CPLX, NN>;                                                   \
         if (set_smem(kern, sm)) return 1;                                                   \
         unsigned grid = (unsigned)((nlines + LPB - 1) / LPB);                               \
         kern<<<grid, ZCfg<NN>::THREADS, sm, st>>>(A, B, dA, dB, line0, oline0, nlines,       \
-            (const C*)c->tw[2], (const C*)c->mult[half][2], c->pol_zin, c->pol_zout);       \
+            (const C*)c->tw[2], (const C*)c->mult[half][2]);                                \
     }
     if (st == c->stream) prof_mark(c, PROF_ZLINE, 0);
     IES_FOR_N(n, Z_CASE)
@@ -512,68 +387,20 @@ int launch_yline_update(Ctx* c, const UpdParams& p, int half) {
     using C = typename Cx<T>::type;
     const int n = c->cfg.ny;
     if (p.i1 <= p.i0) return 0;
-    const bool hint = (p.pol_dz | p.pol_g) != 0;
-    int tsm = 0;
-    if (const char* e = getenv("IES_B200_TABLES_SMEM")) tsm = atoi(e);
+    const bool pal = p.Cidx != nullptr;
 #define Y_CASE(NN) {                                                                        \
         using S = SCfg<T, CPLX, NN>;                                                        \
-        size_t sm = sizeof(C) * ((tsm ? 2 * NN : 0) + (size_t)NN * S::W * Fld<T, CPLX>::NF); \
-        auto kern = hint ? k_yline_update<T, CPLX, NN, true> : k_yline_update<T, CPLX, NN, false>; \
+        size_t sm = sizeof(C) * ((size_t)NN * S::W * Fld<T, CPLX>::NF);                     \
+        auto kern = pal ? k_yline_update<T, CPLX, NN, true> : k_yline_update<T, CPLX, NN, false>; \
         if (set_smem(kern, sm)) return 1;                                                   \
         dim3 grid((unsigned)((c->cfg.nz + S::W - 1) / S::W), (unsigned)(p.i1 - p.i0));      \
         kern<<<grid, S::THREADS, sm, c->stream>>>(p, (const C*)c->tw[1],                     \
-            (const C*)c->mult[half][1], tsm);                                               \
+            (const C*)c->mult[half][1]);                                                    \
     }
     prof_mark(c, PROF_YLINE_UPDATE, 0);
     IES_FOR_N(n, Y_CASE)
     prof_mark(c, PROF_YLINE_UPDATE, 1);
 #undef Y_CASE
-    count_launch();
-    IES_CUDA(cudaGetLastError());
-    return 0;
-}
-
-// Returns 0 = launched, 1 = error, 2 = configuration not covered by the fused kernel.
-template <typename T, bool CPLX>
-int launch_shpf_fused(Ctx* c, const UpdParams& p, int half) {
-    using C = typename Cx<T>::type;
-    const int n = c->cfg.ny;
-    if (c->cfg.nz != n || n < 64 || n > 512) return 2;
-    FusedPlan& fp = c->fused;
-    if (!fp.ready) return 2;
-    FusedArgs fa;
-    fa.total = fp.total;
-    fa.ctr = fp.ctr; fa.nc = fp.nc; fa.cx = fp.cx; fa.la = fp.la; fa.slots = fp.slots; fa.kblocks = fp.kblocks; fa.zitems_full = fp.zitems_full;
-    fa.debug_skip = 0;
-    if (const char* e = getenv("IES_B200_FUSED_SKIP")) fa.debug_skip = atoi(e);
-    UpdParams q = p;
-    q.dz[0] = fp.ring[0]; q.dz[1] = fp.ring[1];
-    IES_CUDA(cudaMemsetAsync(fp.ctr, 0, sizeof(int) * (size_t)(1 + 2 * fp.nc), c->stream));
-    prof_mark(c, PROF_YLINE_UPDATE, 0);
-#define F_CASE(NN) {                                                                        \
-        using S = SCfg<T, CPLX, NN>;                                                        \
-        size_t xz = (size_t)ZCfg<NN>::LPB * XchgContig<C, NN>::LS;                          \
-        size_t xy = (size_t)NN * S::W * Fld<T, CPLX>::NF;                                   \
-        size_t sm = sizeof(C) * (4 * NN + (xz > xy ? xz : xy));                             \
-        auto kern = k_shpf_fused<T, CPLX, NN>;                                              \
-        if (set_smem(kern, sm)) return 1;                                                   \
-        if (fp.grid[half] == 0) {                                                           \
-            int per = 0, nsm = 0;                                                           \
-            IES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, 256, sm));   \
-            IES_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, c->cfg.device)); \
-            if (per < 1) { set_error("fused kernel does not fit on an SM"); return 1; }     \
-            fp.grid[half] = per * nsm;                                                      \
-        }                                                                                   \
-        kern<<<fp.grid[half], 256, sm, c->stream>>>(q, fa, (const C*)c->tw[2],               \
-            (const C*)c->mult[half][2], (const C*)c->tw[1], (const C*)c->mult[half][1]);    \
-    }
-    switch (n) {
-        case 64: F_CASE(64); break;   case 128: F_CASE(128); break;
-        case 256: F_CASE(256); break; case 512: F_CASE(512); break;
-        default: return 2;
-    }
-#undef F_CASE
-    prof_mark(c, PROF_YLINE_UPDATE, 1);
     count_launch();
     IES_CUDA(cudaGetLastError());
     return 0;

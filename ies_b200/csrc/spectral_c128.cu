@@ -5,5 +5,4 @@ template int launch_zline<double, true>(Ctx*, const void*, const void*, void*, v
 template int launch_sline<double, true>(Ctx*, const void*, const void*, void*, void*, int, int, int, int);
 template int launch_shpf_half<double, true>(Ctx*, const UpdParams&, int);
 template int launch_yline_update<double, true>(Ctx*, const UpdParams&, int);
-template int launch_shpf_fused<double, true>(Ctx*, const UpdParams&, int);
 }  // namespace ies

@@ -5,5 +5,4 @@ template int launch_zline<float, true>(Ctx*, const void*, const void*, void*, vo
 template int launch_sline<float, true>(Ctx*, const void*, const void*, void*, void*, int, int, int, int);
 template int launch_shpf_half<float, true>(Ctx*, const UpdParams&, int);
 template int launch_yline_update<float, true>(Ctx*, const UpdParams&, int);
-template int launch_shpf_fused<float, true>(Ctx*, const UpdParams&, int);
 }  // namespace ies

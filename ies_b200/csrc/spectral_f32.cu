@@ -5,5 +5,4 @@ template int launch_zline<float, false>(Ctx*, const void*, const void*, void*, v
 template int launch_sline<float, false>(Ctx*, const void*, const void*, void*, void*, int, int, int, int);
 template int launch_shpf_half<float, false>(Ctx*, const UpdParams&, int);
 template int launch_yline_update<float, false>(Ctx*, const UpdParams&, int);
-template int launch_shpf_fused<float, false>(Ctx*, const UpdParams&, int);
 }  // namespace ies

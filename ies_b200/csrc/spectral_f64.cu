@@ -5,5 +5,4 @@ template int launch_zline<double, false>(Ctx*, const void*, const void*, void*, 
 template int launch_sline<double, false>(Ctx*, const void*, const void*, void*, void*, int, int, int, int);
 template int launch_shpf_half<double, false>(Ctx*, const UpdParams&, int);
 template int launch_yline_update<double, false>(Ctx*, const UpdParams&, int);
-template int launch_shpf_fused<double, false>(Ctx*, const UpdParams&, int);
 }  // namespace ies

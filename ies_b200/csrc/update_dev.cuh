@@ -2,7 +2,6 @@
 // (space.py:801-825, 1017-1037 main update; 1110-1712 CPML faces).
 #pragma once
 #include "engine.h"
-#include "mem_hint.cuh"
 
 namespace ies {
 
@@ -70,16 +69,6 @@ template <> struct Vec<double, false> {
     static __device__ __forceinline__ void st(void* p, size_t i, const double (&o)[2]) {
         *reinterpret_cast<double2*>((double*)p + i) = make_double2(o[0], o[1]);
     }
-    template <bool CG> static __device__ __forceinline__ void ldx(const void* p, size_t i, double (&o)[2]) {
-        if (CG) { const double2 v = __ldcg(reinterpret_cast<const double2*>((const double*)p + i)); o[0] = v.x; o[1] = v.y; }
-        else ld(p, i, o);
-    }
-    template <bool HINT> static __device__ __forceinline__ void ldp(const void* p, size_t i, double (&o)[2], uint64_t pol) {
-        const double2 v = ld_pol<HINT>(reinterpret_cast<const double2*>((const double*)p + i), pol); o[0] = v.x; o[1] = v.y;
-    }
-    template <bool HINT> static __device__ __forceinline__ void stp(void* p, size_t i, const double (&o)[2], uint64_t pol) {
-        st_pol<HINT>(reinterpret_cast<double2*>((double*)p + i), make_double2(o[0], o[1]), pol);
-    }
 };
 template <> struct Vec<float, false> {
     static constexpr int V = 4;
@@ -89,18 +78,6 @@ template <> struct Vec<float, false> {
     }
     static __device__ __forceinline__ void st(void* p, size_t i, const double (&o)[4]) {
         *reinterpret_cast<float4*>((float*)p + i) = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
-    }
-    template <bool CG> static __device__ __forceinline__ void ldx(const void* p, size_t i, double (&o)[4]) {
-        if (CG) { const float4 v = __ldcg(reinterpret_cast<const float4*>((const float*)p + i));
-                  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
-        else ld(p, i, o);
-    }
-    template <bool HINT> static __device__ __forceinline__ void ldp(const void* p, size_t i, double (&o)[4], uint64_t pol) {
-        const float4 v = ld_pol<HINT>(reinterpret_cast<const float4*>((const float*)p + i), pol);
-        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-    }
-    template <bool HINT> static __device__ __forceinline__ void stp(void* p, size_t i, const double (&o)[4], uint64_t pol) {
-        st_pol<HINT>(reinterpret_cast<float4*>((float*)p + i), make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]), pol);
     }
 };
 template <> struct Vec<float, true> {
@@ -113,56 +90,34 @@ template <> struct Vec<float, true> {
         *reinterpret_cast<float4*>((float2*)p + i) =
             make_float4((float)o[0].x, (float)o[0].y, (float)o[1].x, (float)o[1].y);
     }
-    template <bool CG> static __device__ __forceinline__ void ldx(const void* p, size_t i, double2 (&o)[2]) {
-        if (CG) { const float4 v = __ldcg(reinterpret_cast<const float4*>((const float2*)p + i));
-                  o[0] = make_double2(v.x, v.y); o[1] = make_double2(v.z, v.w); }
-        else ld(p, i, o);
-    }
-    template <bool HINT> static __device__ __forceinline__ void ldp(const void* p, size_t i, double2 (&o)[2], uint64_t pol) {
-        const float4 v = ld_pol<HINT>(reinterpret_cast<const float4*>((const float2*)p + i), pol);
-        o[0] = make_double2(v.x, v.y); o[1] = make_double2(v.z, v.w);
-    }
-    template <bool HINT> static __device__ __forceinline__ void stp(void* p, size_t i, const double2 (&o)[2], uint64_t pol) {
-        st_pol<HINT>(reinterpret_cast<float4*>((float2*)p + i),
-               make_float4((float)o[0].x, (float)o[0].y, (float)o[1].x, (float)o[1].y), pol);
-    }
 };
 template <> struct Vec<double, true> {
     static constexpr int V = 1;
     static __device__ __forceinline__ void ld(const void* p, size_t i, double2 (&o)[1]) { o[0] = ((const double2*)p)[i]; }
     static __device__ __forceinline__ void st(void* p, size_t i, const double2 (&o)[1]) { ((double2*)p)[i] = o[0]; }
-    template <bool CG> static __device__ __forceinline__ void ldx(const void* p, size_t i, double2 (&o)[1]) {
-        if (CG) o[0] = __ldcg((const double2*)p + i); else ld(p, i, o);
-    }
-    template <bool HINT> static __device__ __forceinline__ void ldp(const void* p, size_t i, double2 (&o)[1], uint64_t pol) {
-        o[0] = ld_pol<HINT>((const double2*)p + i, pol);
-    }
-    template <bool HINT> static __device__ __forceinline__ void stp(void* p, size_t i, const double2 (&o)[1], uint64_t pol) {
-        st_pol<HINT>((double2*)p + i, o[0], pol);
-    }
 };
 // Coefficients of V consecutive cells: from the palette form (one index byte per cell, the
-// 2 KB palette stays in L1) when present, else from the f64 array.
-template <int V> __device__ __forceinline__ void ld_coeff(const UpdParams& q, size_t i, double (&o)[V]) {
-    if (q.Cidx != nullptr) {
-        if constexpr (V == 1) { o[0] = __ldg(q.Cpal + q.Cidx[i]); }
+// palette in the kernel-parameter constant bank) when PAL, else from the f64 array.
+template <int V, bool PAL> __device__ __forceinline__ void ld_coeff(const UpdParams& q, size_t i, double (&o)[V]) {
+    if constexpr (PAL) {
+        if constexpr (V == 1) { o[0] = q.cpal[q.Cidx[i]]; }
         else if constexpr (V == 2) {
             const unsigned short w = *reinterpret_cast<const unsigned short*>(q.Cidx + i);
-            o[0] = __ldg(q.Cpal + (w & 0xff)); o[1] = __ldg(q.Cpal + (w >> 8));
+            o[0] = q.cpal[w & 0xff]; o[1] = q.cpal[w >> 8];
         } else {
             static_assert(V == 1 || V == 2 || V == 4, "vector width");
             const unsigned w = *reinterpret_cast<const unsigned*>(q.Cidx + i);
 #pragma unroll
-            for (int v = 0; v < V; ++v) o[v] = __ldg(q.Cpal + ((w >> (8 * v)) & 0xff));
+            for (int v = 0; v < V; ++v) o[v] = q.cpal[(w >> (8 * v)) & 0xff];
         }
-        return;
-    }
-    const double* p = q.C;
-    if constexpr (V == 1) { o[0] = p[i]; }
-    else {
+    } else {
+        const double* p = q.C;
+        if constexpr (V == 1) { o[0] = p[i]; }
+        else {
 #pragma unroll
-        for (int v = 0; v < V; v += 2) {
-            const double2 t = *reinterpret_cast<const double2*>(p + i + v); o[v] = t.x; o[v + 1] = t.y;
+            for (int v = 0; v < V; v += 2) {
+                const double2 t = *reinterpret_cast<const double2*>(p + i + v); o[v] = t.x; o[v + 1] = t.y;
+            }
         }
     }
 }
@@ -208,7 +163,7 @@ __device__ __forceinline__ void cell_update_regs(const UpdParams& p, unsigned ma
 }
 
 // Scalar per-cell variant (loads and stores the field itself).
-template <typename T, bool CPLX>
+template <typename T, bool CPLX, bool PAL>
 __device__ __forceinline__ void cell_update(const UpdParams& p, unsigned mask, int i, int j, int k,
                                             const typename AccT<CPLX>::type (&d)[6]) {
     using A = typename AccT<CPLX>::type;
@@ -218,7 +173,7 @@ __device__ __forceinline__ void cell_update(const UpdParams& p, unsigned mask, i
 #pragma unroll
     for (int c = 0; c < 3; ++c) g[c] = E::ld(p.G[c], idx);
     double cf[1];
-    ld_coeff<1>(p, idx, cf);
+    ld_coeff<1, PAL>(p, idx, cf);
     cell_update_regs<T, CPLX>(p, mask, i, j, k, cf[0], d, g);
 #pragma unroll
     for (int c = 0; c < 3; ++c) E::st(p.G[c], idx, g[c]);

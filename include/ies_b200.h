@@ -74,9 +74,10 @@ int ies_destroy(ies_ctx* ctx);
 int ies_set_stream(ies_ctx* ctx, void* cuda_stream);
 int ies_sync(ies_ctx* ctx);
 /* Engine tuning knobs (no reference counterpart; defaults need no call).  Names:
- * "chunk" (x planes per z-line / y-line launch pair of the SHPF half-step, 0 = whole slab),
- * "chunk_slots", "two_stream", "graph", "l2_window", "pol_zin", "pol_zout", "pol_dz",
- * "pol_g" (L2 eviction policy: 0 none, 1 evict_last, 2 evict_first), "fused", "l2_reset". */
+ * "alt" (1 = one alternating-orientation kernel per SHPF half-step, 0 = z-line + y-line
+ * kernel pair), "palette" (1 = palette-compressed coefficient arrays when they hold
+ * <= 256 distinct values), "prefetch" (1 = CTAs prefetch their streaming operands into L2),
+ * "reset_psi" (zero the CPML auxiliary arrays). */
 int ies_set_option(ies_ctx* ctx, const char* name, int64_t value);
 
 /* ---- setup --------------------------------------------------------------- */

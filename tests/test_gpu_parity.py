@@ -36,18 +36,6 @@ def test_case_vs_oracle_live(product, name):
     assert max(errs.values()) <= H.tolerance(case), (name, errs)
 
 
-@pytest.mark.parametrize('name', ['shpf_f64_xpml_64', 'shpf_f64_allpml_64_r2', 'shpf_c64_xpml_64'])
-def test_two_kernel_path_matches_fused(product, name, monkeypatch):
-    """The fused persistent SHPF half-step and the two-kernel path give the same fields."""
-    case = C.CASES_BY_NAME[name]
-    monkeypatch.setenv('IES_B200_FUSED', '1')
-    a = H.run_product(product, case)
-    monkeypatch.setenv('IES_B200_FUSED', '0')
-    b = H.run_product(product, case)
-    for n in C.FIELDS:
-        assert np.array_equal(np.asarray(a[n]), np.asarray(b[n])), n
-
-
 ALT_CASES = ['shpf_f64_xpml', 'shpf_f32_xpml', 'shpf_c64_xpml', 'shpf_c128_bloch_yz', 'shpf_f64_allpml_r2',
              'shpf_f64_ypml_only', 'shpf_f64_xpml_64', 'shpf_f32_allpml_64', 'shpf_c128_bloch_yz_128',
              'shpf_f64_xpml_16x64', 'shpf_f64_src_ez', 'shpf_f64_src_ex_hard', 'shpf_f64_src_hy_r2',

@@ -21,30 +21,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
-HINT_SCRATCH = dict(pol_zout=1, pol_dz=1)
 VARIANTS = [
-    ('base', {}),
-    ('chunk18', dict(chunk=18)),
-    ('chunk37', dict(chunk=37)),
-    ('chunk18_hs', dict(chunk=18, **HINT_SCRATCH)),
-    ('chunk37_hs', dict(chunk=37, **HINT_SCRATCH)),
-    ('chunk18_hs_g2', dict(chunk=18, pol_g=2, **HINT_SCRATCH)),
-    ('chunk18_hs_zin', dict(chunk=18, pol_zin=1, **HINT_SCRATCH)),
-    ('chunk18_win', dict(chunk=18, l2_window=1)),
-    ('chunk37_win', dict(chunk=37, l2_window=1)),
-    ('ts18', dict(chunk=18, two_stream=1, chunk_slots=3)),
-    ('ts18_graph', dict(chunk=18, two_stream=1, chunk_slots=3, graph=1)),
-    ('ts18_graph_hs', dict(chunk=18, two_stream=1, chunk_slots=3, graph=1, **HINT_SCRATCH)),
-    ('ts18_graph_hs_g2', dict(chunk=18, two_stream=1, chunk_slots=3, graph=1, pol_g=2, **HINT_SCRATCH)),
-    ('ts18_graph_hs_zin', dict(chunk=18, two_stream=1, chunk_slots=3, graph=1, pol_zin=1, **HINT_SCRATCH)),
-    ('ts18_graph_win', dict(chunk=18, two_stream=1, chunk_slots=3, graph=1, l2_window=1)),
-    ('ts9_graph_hs', dict(chunk=9, two_stream=1, chunk_slots=4, graph=1, **HINT_SCRATCH)),
-    ('ts37_graph_hs', dict(chunk=37, two_stream=1, chunk_slots=2, graph=1, **HINT_SCRATCH)),
-    ('ts37_graph_win', dict(chunk=37, two_stream=1, chunk_slots=2, graph=1, l2_window=1)),
-    ('hints_only_g2', dict(pol_g=2)),
+    ('base', dict(alt=0, palette=1)),
+    ('base_nopal', dict(alt=0, palette=0)),
+    ('alt', dict(alt=1, palette=1)),
+    ('alt_nopal', dict(alt=1, palette=0)),
 ]
-ALL_OPTS = ('chunk', 'chunk_slots', 'two_stream', 'graph', 'l2_window', 'pol_zin', 'pol_zout', 'pol_dz', 'pol_g')
-DEFAULTS = dict(chunk=0, chunk_slots=3, two_stream=0, graph=0, l2_window=0, pol_zin=0, pol_zout=0, pol_dz=0, pol_g=0)
+ALL_OPTS = ('alt', 'palette', 'prefetch')
+DEFAULTS = dict(alt=1, palette=1, prefetch=0)
 
 
 def main():
@@ -72,6 +56,7 @@ def main():
     ncell = sp.myNx * bench.NY * bench.NZ
 
     def upload():
+        _lib.check(lib.ies_set_option(sp._ctx, b'reset_psi', 1))
         for n, a in init.items():
             _lib.check(lib.ies_set_field(sp._ctx, _lib.COMP[n], _lib.I3(0, 0, 0), _lib.I3(*sp.loc_grid),
                                          a.ctypes.data_as(C.c_void_p)))
@@ -109,6 +94,9 @@ def main():
                 sig = signature()
                 if name == 'base': ref_sig = sig
                 sig_ok = bool(np.array_equal(sig, ref_sig)) if ref_sig is not None else None
+                if ref_sig is not None and not sig_ok:
+                    print('max abs diff vs base', float(np.max(np.abs(sig - ref_sig))), 'per plane',
+                          [float(np.max(np.abs(a - b))) for a, b in zip(sig, ref_sig)], flush=True)
             for t in range(args.warmup): step(t)
             sp.sync()
             _lib.check(lib.ies_timer_start(sp._ctx))
