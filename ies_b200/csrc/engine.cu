@@ -439,7 +439,7 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     const size_t fbytes = ncell * c->esize;
     for (int q = 0; q < 6; ++q) if (dev_alloc(c, &c->F[q], fbytes)) return 1;
     for (int h = 0; h < 2; ++h) { c->C[h] = nullptr; c->Cidx[h] = nullptr; c->Cpal[h] = nullptr; c->Cnpal[h] = 0; }
-    c->use_palette = 1;
+    c->use_palette = 0;     // measured slower than the f64 array (index -> value dependent loads), kept as an option
     if (const char* e = getenv("IES_B200_PALETTE")) c->use_palette = atoi(e);
     for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
     // spectral scratch is allocated on first use

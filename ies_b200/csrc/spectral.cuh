@@ -141,49 +141,17 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 }
 
 // ------------------------------------------ y lines + fused field update -----
-// L2 prefetch of a tile's rows (row_bytes each, rows row_stride bytes apart): one
-// prefetch.global.L2 per 128-byte line, spread over the CTA.  Fire-and-forget: the tile's
-// later loads find their lines in L2 instead of paying the HBM latency inside the batch.
-__device__ __forceinline__ void prefetch_rows_l2(const void* base, size_t first_byte, int rows,
-                                                 int row_bytes, size_t row_stride) {
-    if (base == nullptr) return;
-    const int lpr = (row_bytes + 127) / 128;
-    const int total = rows * lpr;
-    for (int l = threadIdx.x; l < total; l += blockDim.x) {
-        const int r = l / lpr, c = l - r * lpr;
-        const char* a = (const char*)base + first_byte + (size_t)r * row_stride + (size_t)c * 128;
-        asm volatile("prefetch.global.L2 [%0];" :: "l"(a));
-    }
-}
-
-// Phase A: W adjacent y lines (one per column, lane = column) are transformed in
-//          registers; the derivative pair lands in shared memory in tile layout
-//          stash[row * W + col].
-// Phase B: the CTA re-maps to 16-byte vectors along z (V cells per thread) and streams
-//          the cell update: PB row groups of loads are issued before any arithmetic so
-//          enough bytes are in flight to cover HBM latency.
-// One CTA = the tile (plane i, columns kb*W .. kb*W+W-1, all rows).  PAL: coefficients come
-// from the palette form (update_dev.cuh ld_coeff).
-template <typename T, bool CPLX, int N, bool PAL>
-__global__ void __launch_bounds__(256, (CPLX ? 1 : 2))
-k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
-               const typename Cx<T>::type* __restrict__ ml) {
+// Phase B of k_yline_update.  FAST: no CPML term touches the tile and every update box either
+// contains or misses it (upd = component mask, CTA-uniform): straight-line interior code.
+template <typename T, bool CPLX, int N, bool PAL, bool FAST>
+__device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, const int k0, const unsigned mask,
+                                              const int upd, const typename Cx<T>::type* xbuf) {
     using C = typename Cx<T>::type;
-    using F = Fld<T, CPLX>;
     using A = typename AccT<CPLX>::type;
     using VV = Vec<T, CPLX>;
     using S = SCfg<T, CPLX, N>;
     constexpr int W = S::W;
     constexpr int V = VV::V;
-    constexpr int NF = F::NF;
-    // The twiddle / multiplier tables are read straight from global memory (L1-resident,
-    // 8 KB): that keeps the CTA at N*W*16 B of shared memory, so two CTAs fit the 132 KB
-    // carve-out and 96 KB of L1 remain for loads in flight (measured: the kernel's
-    // bandwidth follows the L1 size left by the carve-out).
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    C* xbuf = reinterpret_cast<C*>(smem_raw);      // NF buffers of N*W: exchange, then derivative stash
-    const int i = p.i0 + (int)blockIdx.y;
-    const int k0 = (int)blockIdx.x * W;
     const size_t plane = (size_t)p.ny * p.nz;
     const int in = i + p.dir;                       // x neighbour plane
     const bool nb_inside = (in >= 0 && in < p.nx);
@@ -191,50 +159,6 @@ k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
     const void* nFy = nb_inside ? p.F[1] : p.halo[0];
     const void* nFz = nb_inside ? p.F[2] : p.halo[1];
     const size_t nbase = nb_inside ? (size_t)in * plane : 0;
-    if (p.prefetch) {
-        constexpr int ES = S::ES;
-        const size_t fb = ((size_t)i * plane + k0) * ES, rs = (size_t)p.nz * ES;
-        const int cols = min(W, p.nz - k0);
-        prefetch_rows_l2(p.dz[0], (size_t)((long long)fb + p.dz_off * ES), N, cols * ES, rs);
-        prefetch_rows_l2(p.dz[1], (size_t)((long long)fb + p.dz_off * ES), N, cols * ES, rs);
-#pragma unroll
-        for (int c = 0; c < 3; ++c) prefetch_rows_l2(p.G[c], fb, N, cols * ES, rs);
-        if (p.pstd) {
-            prefetch_rows_l2(p.dxs[0], fb, N, cols * ES, rs);
-            prefetch_rows_l2(p.dxs[1], fb, N, cols * ES, rs);
-        } else if (nb_any) {
-            prefetch_rows_l2(p.F[1], fb, N, cols * ES, rs);
-            prefetch_rows_l2(nFy, (nbase + k0) * ES, N, cols * ES, rs);
-            prefetch_rows_l2(nFz, (nbase + k0) * ES, N, cols * ES, rs);
-        }
-        if (!PAL) prefetch_rows_l2(p.C, ((size_t)i * plane + k0) * 8, N, cols * 8, (size_t)p.nz * 8);
-    }
-    {
-        const int c = threadIdx.x % W, t = threadIdx.x / W;
-        const int k = k0 + c;
-        const bool ok = k < p.nz;
-        const size_t pbase = (size_t)i * plane + k;
-        // pair (F_z, F_x): Re -> d/dy F_z (slot 0), Im -> d/dy F_x (slot 5)
-#pragma unroll
-        for (int f = 0; f < NF; ++f) {
-            XchgStrided<C, W> xb{xbuf + (size_t)f * N * W + c};
-            C v[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                if (ok) v[q] = F::ld(p.F[2], p.F[0], pbase + (size_t)line_index<N>(t, q) * p.nz, f);
-                else { v[q].x = 0; v[q].y = 0; }
-            }
-            fft_forward<N>(v, t, tw, xb);
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], ml[spec_index<N>(t, q)]);
-            fft_inverse<N>(v, t, tw, xb);
-            __syncthreads();                 // everyone finished reading the exchange buffer
-#pragma unroll
-            for (int q = 0; q < 16; ++q) xb.st(line_index<N>(t, q), v[q]);
-        }
-        __syncthreads();
-    }
-    // ---------------- phase B: vectorised streaming update ----------------
     constexpr int CG = W / V;                    // column groups
     constexpr int RP = S::THREADS / CG;          // rows per pass
     constexpr int NPASS = N / RP;
@@ -242,7 +166,6 @@ k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
     const int cg = threadIdx.x % CG, tr = threadIdx.x / CG;
     const int k = k0 + cg * V;
     if (k >= p.nz) return;
-    const unsigned mask = term_mask(p, i, i + 1, 0, p.ny, k0, k0 + W);
     const double sx = p.dir > 0 ? p.rdx : -p.rdx;
 #pragma unroll 1
     for (int pass0 = 0; pass0 < NPASS; pass0 += PB) {
@@ -291,13 +214,75 @@ k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
                     d[4] = a_scale(sx, a_sub(a4[u][v], b4[u][v]));
                 } else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
                 A gg[3] = {g[u][0][v], g[u][1][v], g[u][2][v]};
-                cell_update_regs<T, CPLX>(p, mask, i, j, k + v, cf[u][v], d, gg);
+                if constexpr (FAST) cell_update_fast<CPLX>(upd, cf[u][v], d, gg);
+                else cell_update_regs<T, CPLX>(p, mask, i, j, k + v, cf[u][v], d, gg);
                 g[u][0][v] = gg[0]; g[u][1][v] = gg[1]; g[u][2][v] = gg[2];
             }
 #pragma unroll
             for (int c = 0; c < 3; ++c) VV::st(p.G[c], idx, g[u][c]);
         }
     }
+}
+
+// Phase A: W adjacent y lines (one per column, lane = column) are transformed in
+//          registers; the derivative pair lands in shared memory in tile layout
+//          stash[row * W + col].
+// Phase B: the CTA re-maps to 16-byte vectors along z (V cells per thread) and streams
+//          the cell update: PB row groups of loads are issued before any arithmetic so
+//          enough bytes are in flight to cover HBM latency.
+// One CTA = the tile (plane i, columns kb*W .. kb*W+W-1, all rows).  PAL: coefficients come
+// from the palette form (update_dev.cuh ld_coeff).
+template <typename T, bool CPLX, int N, bool PAL>
+__global__ void __launch_bounds__(256, (CPLX ? 1 : 2))
+k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
+               const typename Cx<T>::type* __restrict__ ml) {
+    using C = typename Cx<T>::type;
+    using F = Fld<T, CPLX>;
+    using A = typename AccT<CPLX>::type;
+    using VV = Vec<T, CPLX>;
+    using S = SCfg<T, CPLX, N>;
+    constexpr int W = S::W;
+    constexpr int V = VV::V;
+    constexpr int NF = F::NF;
+    // The twiddle / multiplier tables are read straight from global memory (L1-resident,
+    // 8 KB): that keeps the CTA at N*W*16 B of shared memory, so two CTAs fit the 132 KB
+    // carve-out and 96 KB of L1 remain for loads in flight (measured: the kernel's
+    // bandwidth follows the L1 size left by the carve-out).
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* xbuf = reinterpret_cast<C*>(smem_raw);      // NF buffers of N*W: exchange, then derivative stash
+    const int i = p.i0 + (int)blockIdx.y;
+    const int k0 = (int)blockIdx.x * W;
+    const size_t plane = (size_t)p.ny * p.nz;
+    {
+        const int c = threadIdx.x % W, t = threadIdx.x / W;
+        const int k = k0 + c;
+        const bool ok = k < p.nz;
+        const size_t pbase = (size_t)i * plane + k;
+        // pair (F_z, F_x): Re -> d/dy F_z (slot 0), Im -> d/dy F_x (slot 5)
+#pragma unroll
+        for (int f = 0; f < NF; ++f) {
+            XchgStrided<C, W> xb{xbuf + (size_t)f * N * W + c};
+            C v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (ok) v[q] = F::ld(p.F[2], p.F[0], pbase + (size_t)line_index<N>(t, q) * p.nz, f);
+                else { v[q].x = 0; v[q].y = 0; }
+            }
+            fft_forward<N>(v, t, tw, xb);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], ml[spec_index<N>(t, q)]);
+            fft_inverse<N>(v, t, tw, xb);
+            __syncthreads();                 // everyone finished reading the exchange buffer
+#pragma unroll
+            for (int q = 0; q < 16; ++q) xb.st(line_index<N>(t, q), v[q]);
+        }
+        __syncthreads();
+    }
+    // ---------------- phase B: vectorised streaming update ----------------
+    const unsigned mask = term_mask(p, i, i + 1, 0, p.ny, k0, k0 + W);
+    const int upd = tile_update_class(p, i, i + 1, 0, p.ny, k0, min(k0 + W, p.nz));
+    if (mask == 0u && upd >= 0) yline_phase_b<T, CPLX, N, PAL, true>(p, i, k0, mask, upd, xbuf);
+    else yline_phase_b<T, CPLX, N, PAL, false>(p, i, k0, mask, upd, xbuf);
 }
 
 // ------------------------------------------------------------- launchers -----

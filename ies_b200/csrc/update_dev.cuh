@@ -162,6 +162,39 @@ __device__ __forceinline__ void cell_update_regs(const UpdParams& p, unsigned ma
     }
 }
 
+// Tile-level classification against the three update boxes: returns the bit mask of the
+// components whose box contains the whole tile [i0,i1) x [j0,j1) x [k0,k1) when every box
+// either contains the tile or misses it completely, else -1 (per-cell tests needed).
+__device__ __forceinline__ int tile_update_class(const UpdParams& p, int i0, int i1, int j0, int j1, int k0, int k1) {
+    int upd = 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const Box& b = p.box[c];
+        const bool inside = b.lo[0] <= i0 && i1 <= b.hi[0] && b.lo[1] <= j0 && j1 <= b.hi[1] && b.lo[2] <= k0 && k1 <= b.hi[2];
+        const bool apart = b.hi[0] <= i0 || i1 <= b.lo[0] || b.hi[1] <= j0 || j1 <= b.lo[1] || b.hi[2] <= k0 || k1 <= b.lo[2];
+        if (inside) upd |= 1 << c;
+        else if (!apart) return -1;
+    }
+    return upd;
+}
+
+// Interior fast path of cell_update_regs: no CPML term touches the tile and the update boxes
+// were resolved per tile (upd = tile_update_class(...) >= 0, CTA-uniform).  Same expression
+// as the general path, so both give identical bits.
+template <bool CPLX>
+__device__ __forceinline__ void cell_update_fast(const int upd, const double C,
+                                                 const typename AccT<CPLX>::type (&d)[6],
+                                                 typename AccT<CPLX>::type (&g)[3]) {
+    if (upd == 7) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g[c] = a_add(g[c], a_scale(C, a_sub(d[2 * c], d[2 * c + 1])));
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (upd & (1 << c)) g[c] = a_add(g[c], a_scale(C, a_sub(d[2 * c], d[2 * c + 1])));
+    }
+}
+
 // Scalar per-cell variant (loads and stores the field itself).
 template <typename T, bool CPLX, bool PAL>
 __device__ __forceinline__ void cell_update(const UpdParams& p, unsigned mask, int i, int j, int k,

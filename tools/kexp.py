@@ -28,7 +28,7 @@ VARIANTS = [
     ('alt_nopal', dict(alt=1, palette=0)),
 ]
 ALL_OPTS = ('alt', 'palette', 'prefetch')
-DEFAULTS = dict(alt=1, palette=1, prefetch=0)
+DEFAULTS = dict(alt=1, palette=0, prefetch=0)
 
 
 def main():
