@@ -313,7 +313,6 @@ static int fill_params(ies_ctx* c, int half, UpdParams& p) {
     p.i0 = 0; p.i1 = c->cfg.nx;
     p.pstd = c->cfg.method == IES_PSTD;
     p.dz_off = 0;
-    p.prefetch = c->prefetch;
     p.rdx = 1.0 / c->cfg.dx; p.rdy = 1.0 / c->cfg.dy; p.rdz = 1.0 / c->cfg.dz;
     p.nterms = (int)c->terms[half].size();
     for (int t = 0; t < p.nterms; ++t) p.terms[t] = c->terms[half][t];
@@ -325,16 +324,6 @@ static int ensure_scratch(ies_ctx* c, int first, int last) {
     for (int q = first; q <= last; ++q)
         if (!c->scratch[q]) if (dev_alloc(c, &c->scratch[q], fbytes)) return 1;
     return 0;
-}
-
-// A field component was written in the x-range [lo, hi) outside the update kernels: if the
-// alternating SHPF path's scratch was derived from it, those planes must be refreshed.
-static void mark_field_written(ies_ctx* c, int comp, int lo, int hi) {
-    const bool hit = (c->scr_kind == SCR_FOR_H && (comp == IES_EZ || comp == IES_EX)) ||
-                     (c->scr_kind == SCR_FOR_E && (comp == IES_HY || comp == IES_HX));
-    if (!hit || hi <= lo) return;
-    if (c->scr_dirty_hi <= c->scr_dirty_lo) { c->scr_dirty_lo = lo; c->scr_dirty_hi = hi; }
-    else { c->scr_dirty_lo = std::min(c->scr_dirty_lo, lo); c->scr_dirty_hi = std::max(c->scr_dirty_hi, hi); }
 }
 
 template <typename T, bool CP>
@@ -372,32 +361,19 @@ static int do_update(ies_ctx* c, int half) {
         if (!c->mult[half][a]) { set_error("spectral multiplier not set (malloc()/init_update_constants() missing)"); return 1; }
     if (ensure_scratch(c, 0, c->cfg.method == IES_PSTD ? 3 : 1)) return 1;
     p.dz[0] = c->scratch[0]; p.dz[1] = c->scratch[1];
-    if (c->cfg.method == IES_SHPF && c->use_alt) {
-        // one kernel per half-step; the scratch holds the derivative pair the previous
-        // half-step's kernel produced from the field it updated (shpf_half.cuh)
-        const int need = half == IES_HALF_H ? SCR_FOR_H : SCR_FOR_E;
-        if (c->scr_kind != need) { c->scr_dirty_lo = 0; c->scr_dirty_hi = nx; }
-        if (c->scr_dirty_hi > c->scr_dirty_lo) {
-            const int lo = c->scr_dirty_lo, hi = c->scr_dirty_hi;
-            if (half == IES_HALF_H) {
-                if (launch_sline<T, CP>(c, p.F[2], p.F[0], c->scratch[0], c->scratch[1], half, 1, lo, hi)) return 1;
-            } else {
-                if (launch_zline<T, CP>(c, p.F[1], p.F[0], c->scratch[0], c->scratch[1], half, lo, hi, lo)) return 1;
-            }
-        }
-        if (launch_shpf_half<T, CP>(c, p, half)) return 1;
-        c->scr_kind = half == IES_HALF_H ? SCR_FOR_E : SCR_FOR_H;
-        c->scr_dirty_lo = c->scr_dirty_hi = 0;
+    if (c->cfg.method == IES_SHPF && c->use_split) {
+        // G_y (+ d/dz F_y -> scratch) in the z-line kernel, G_x and G_z in the y-line kernel
+        if (launch_zline_update<T, CP>(c, p, half)) return 1;
+        if (launch_yline_update<T, CP>(c, p, half, true)) return 1;
         return 0;
     }
-    c->scr_kind = SCR_NONE;
     p.dxs[0] = c->scratch[2]; p.dxs[1] = c->scratch[3];
     if (c->cfg.method == IES_PSTD) {
         if (!c->mult[half][0]) { set_error("x multiplier not set"); return 1; }
         if (launch_sline<T, CP>(c, p.F[2], p.F[1], c->scratch[2], c->scratch[3], half, 0, 0, nx)) return 1;
     }
     if (launch_zline<T, CP>(c, p.F[1], p.F[0], c->scratch[0], c->scratch[1], half, 0, nx, 0)) return 1;
-    if (launch_yline_update<T, CP>(c, p, half)) return 1;
+    if (launch_yline_update<T, CP>(c, p, half, false)) return 1;
     return 0;
 }
 
@@ -443,11 +419,8 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     if (const char* e = getenv("IES_B200_PALETTE")) c->use_palette = atoi(e);
     for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
     // spectral scratch is allocated on first use
-    c->prefetch = 0;
-    if (const char* e = getenv("IES_B200_PREFETCH")) c->prefetch = atoi(e);
-    c->use_alt = 1;
-    if (const char* e = getenv("IES_B200_ALT")) c->use_alt = atoi(e);
-    c->scr_kind = SCR_NONE; c->scr_dirty_lo = c->scr_dirty_hi = 0;
+    c->use_split = 0;     // measured: split 3.43 ms/step vs 3.19 (the z-line kernel does not overlap its streaming with the FFT)
+    if (const char* e = getenv("IES_B200_SPLIT")) c->use_split = atoi(e);
     const size_t pbytes = (size_t)cfg->ny * cfg->nz * c->esize;
     for (int h = 0; h < 2; ++h) for (int w = 0; w < 2; ++w) if (dev_alloc(c, &c->halo_recv[h][w], pbytes)) return 1;
     for (int h = 0; h < 2; ++h) for (int a = 0; a < 3; ++a) c->mult[h][a] = nullptr;
@@ -501,8 +474,7 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     IES_CUDA(cudaSetDevice(c->cfg.device));
     IES_CUDA(cudaStreamSynchronize(c->stream));
     if (n == "palette") c->use_palette = v;
-    else if (n == "alt") { c->use_alt = v; c->scr_kind = SCR_NONE; }
-    else if (n == "prefetch") c->prefetch = v;
+    else if (n == "split") c->use_split = v;
     else if (n == "reset_psi") {               // zero the CPML auxiliary state (restart a run on new fields)
         for (int h = 0; h < 2; ++h)
             for (const PmlTermDev& t : c->terms[h])
@@ -561,6 +533,7 @@ int ies_set_coeff(ies_ctx* c, int half, const double* host, int64_t n) {
     // palette form: materials are piecewise constant, so the array usually holds a handful of
     // distinct values; the update kernels then read one index byte per cell instead of 8 bytes
     c->Cnpal[half] = 0;
+    if (!c->use_palette) return 0;
     if (!c->Cidx[half]) {
         void* p; if (dev_alloc(c, &p, ncell, false)) return 1; c->Cidx[half] = (uint8_t*)p;
         if (dev_alloc(c, &p, 257 * 8, false)) return 1; c->Cpal[half] = (double*)p;
@@ -596,7 +569,6 @@ int ies_set_update_box(ies_ctx* c, int comp, const int32_t lo[3], const int32_t 
 }
 
 int ies_set_multiplier(ies_ctx* c, int half, int axis, const double* re_im, int32_t n) {
-    c->scr_kind = SCR_NONE;
     const int dims[3] = {c->cfg.nx, c->cfg.ny, c->cfg.nz};
     if (half < 0 || half > 1 || axis < 0 || axis > 2 || n != dims[axis]) { set_error("ies_set_multiplier: bad args"); return 1; }
     if (!fft_len_supported(n)) { set_error("ies_set_multiplier: unsupported length"); return 1; }
@@ -715,7 +687,6 @@ int ies_put_src(ies_ctx* c, int comp, const int32_t lo[3], const int32_t hi[3], 
     const long n = (long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
     if (n <= 0) return 0;
     IES_CUDA(cudaSetDevice(c->cfg.device));
-    mark_field_written(c, comp, lo[0], hi[0]);
     double2 *dpx = nullptr, *dpy = nullptr, *dpz = nullptr;
     void* tmp = nullptr;
     if (px && py && pz) {
@@ -781,7 +752,6 @@ int ies_set_field(ies_ctx* c, int comp, const int32_t lo[3], const int32_t hi[3]
     const long n = (long)(hi[0] - lo[0]) * (hi[1] - lo[1]) * (hi[2] - lo[2]);
     if (n <= 0) return 0;
     IES_CUDA(cudaSetDevice(c->cfg.device));
-    mark_field_written(c, comp, lo[0], hi[0]);
     const bool whole_planes = lo[1] == 0 && lo[2] == 0 && hi[1] == c->cfg.ny && hi[2] == c->cfg.nz;
     if (whole_planes) {
         const size_t pb = (size_t)c->cfg.ny * c->cfg.nz * c->esize;
@@ -798,7 +768,6 @@ int ies_set_field(ies_ctx* c, int comp, const int32_t lo[3], const int32_t hi[3]
 int ies_field_ptr(ies_ctx* c, int comp, void** dev) {
     if (comp < 0 || comp > 5) { set_error("bad component"); return 1; }
     *dev = c->F[comp];
-    c->scr_kind = SCR_NONE;            // the caller may write through the pointer
     return 0;
 }
 

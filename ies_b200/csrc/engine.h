@@ -41,7 +41,6 @@ struct UpdParams {
     int i0, i1;                 // x range handled by this launch
     int pstd;                   // x derivative comes from dxs[]
     long long dz_off;           // element offset of the dz scratch relative to the field index
-    int prefetch;               // 1: CTAs prefetch their streaming operands into L2 at start
     double rdx, rdy, rdz;
     Box box[3];
     int nterms;
@@ -75,15 +74,9 @@ struct Ctx {
     cudaEvent_t ev_t0, ev_t1;          // ies_timer_start/stop
     int profiling;                     // per-kernel CUDA-event timing on/off
     std::vector<cudaEvent_t> prof_ev[4][2];   // [slot][begin/end]
-    int prefetch;                      // UpdParams::prefetch
-    // alternating-orientation SHPF path (shpf_half.cuh): what the scratch pair currently holds
-    // and the x-range in which it is stale (fields written since it was produced)
-    int use_alt;
-    int scr_kind;                      // SCR_NONE / SCR_FOR_H (d/dy of E_z,E_x) / SCR_FOR_E (d/dz of H_y,H_x)
-    int scr_dirty_lo, scr_dirty_hi;
+    int use_split;                     // SHPF: 1 = split update (shpf_split.cuh), 0 = z-line + full y-line kernels
 };
 
-enum { SCR_NONE = 0, SCR_FOR_H = 1, SCR_FOR_E = 2 };
 enum { PROF_ZLINE = 0, PROF_YLINE_UPDATE = 1, PROF_XLINE = 2, PROF_FDTD = 3 };
 void prof_mark(Ctx* c, int slot, int end);
 
@@ -100,9 +93,9 @@ int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
 template <typename T, bool CPLX>
 int launch_sline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int axis, int i0, int i1);
 template <typename T, bool CPLX>
-int launch_shpf_half(Ctx* c, const UpdParams& p, int half);
+int launch_zline_update(Ctx* c, const UpdParams& p, int half);     // shpf_split.cuh
 template <typename T, bool CPLX>
-int launch_yline_update(Ctx* c, const UpdParams& p, int half);
+int launch_yline_update(Ctx* c, const UpdParams& p, int half, bool split);
 
 bool fft_len_supported(int n);
 

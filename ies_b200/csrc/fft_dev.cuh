@@ -77,23 +77,28 @@ template <int R, bool INV, typename C> struct Dft {
     }
 };
 
-template <int N> struct Plan {
+// Radix plan for VPT register values per thread (VPT = 16: radix 16/16/(N/256), one line =
+// N/16 threads; VPT = 8: radix 8/8/(N/64), one line = N/8 threads, half the registers).
+template <int N, int VPT> struct PlanV {
     static_assert(N >= 16 && N <= 1024 && (N & (N - 1)) == 0, "FFT length must be 16..1024, power of two");
-    static constexpr int T  = N / 16;                        // threads per line
-    static constexpr int R1 = (N / 16 >= 16) ? 16 : N / 16;  // second radix (1 if N == 16)
-    static constexpr int R2 = N / (16 * R1);                 // third radix (1, 2 or 4)
-    static constexpr int RL = (R2 > 1) ? R2 : (R1 > 1 ? R1 : 16);   // radix adjacent to the spectrum
+    static_assert(VPT == 8 || VPT == 16, "values per thread");
+    static constexpr int T  = N / VPT;                           // threads per line
+    static constexpr int R1 = (N / VPT >= VPT) ? VPT : N / VPT;  // second radix (1 if N == VPT)
+    static constexpr int R2 = N / (VPT * R1);                    // third radix
+    static_assert(R2 <= VPT, "FFT length too large for this plan");
+    static constexpr int RL = (R2 > 1) ? R2 : (R1 > 1 ? R1 : VPT);   // radix adjacent to the spectrum
 };
+template <int N> using Plan = PlanV<N, 16>;
 
-// One Stockham stage on the 16 register values of a thread.
-//   v[b*R + m] <-> input element  j + m*N/R,  j = t + T*b   (b < 16/R butterflies per thread)
+// One Stockham stage on the VPT register values of a thread.
+//   v[b*R + m] <-> input element  j + m*N/R,  j = t + T*b   (b < VPT/R butterflies per thread)
 // LOAD : read inputs from the exchange buffer;  STORE: write outputs to it at
 //   (j/NS)*NS*R + (j%NS) + m*NS.   Without STORE the outputs stay in v[b*R+m].
-// tw: master twiddle table W_N[k] = exp(-2 pi i k/N) (shared memory).
-template <int N, int R, int NS, bool INV, bool LOAD, bool STORE, typename C, typename X>
-__device__ __forceinline__ void fft_stage(C (&v)[16], const int t, const C* __restrict__ tw, X& xb) {
-    constexpr int T = N / 16;
-    constexpr int NB = 16 / R;
+// tw: master twiddle table W_N[k] = exp(-2 pi i k/N) (shared or global memory).
+template <int N, int VPT, int R, int NS, bool INV, bool LOAD, bool STORE, bool TWT = false, typename C, typename X>
+__device__ __forceinline__ void fft_stage_v(C (&v)[VPT], const int t, const C* __restrict__ tw, X& xb) {
+    constexpr int T = N / VPT;
+    constexpr int NB = VPT / R;
     if (LOAD) {
         xb.sync();
 #pragma unroll
@@ -115,7 +120,10 @@ __device__ __forceinline__ void fft_stage(C (&v)[16], const int t, const C* __re
             constexpr int step = N / (NS * R);
 #pragma unroll
             for (int m = 1; m < R; ++m) {
-                const C w = tw[(jj * m * step) & (N - 1)];
+                // TWT: tw is the stage table transposed to [m][jj] (consecutive threads read
+                // consecutive entries: no shared-memory bank conflicts); only valid when all
+                // twiddled stages of the plan share one (R, NS) pair, e.g. N = VPT * VPT
+                const C w = TWT ? tw[m * NS + jj] : tw[(jj * m * step) & (N - 1)];
                 in[m] = INV ? cmulc(in[m], w) : cmul(in[m], w);
             }
         }
@@ -132,46 +140,54 @@ __device__ __forceinline__ void fft_stage(C (&v)[16], const int t, const C* __re
 }
 
 // Spectrum index held in v[q] after fft_forward (and expected by fft_inverse).
-template <int N> __device__ __forceinline__ int spec_index(int t, int q) {
-    constexpr int RL = Plan<N>::RL;
-    constexpr int T = N / 16;
+template <int N, int VPT> __device__ __forceinline__ int spec_index_v(int t, int q) {
+    constexpr int RL = PlanV<N, VPT>::RL;
+    constexpr int T = N / VPT;
     const int b = q / RL, m = q % RL;
     return t + T * b + m * (N / RL);
 }
 // Line index held in v[q] before fft_forward and after fft_inverse.
-template <int N> __device__ __forceinline__ int line_index(int t, int q) { return t + q * (N / 16); }
+template <int N, int VPT> __device__ __forceinline__ int line_index_v(int t, int q) { return t + q * (N / VPT); }
 
-template <int N, typename C, typename X>
-__device__ __forceinline__ void fft_forward(C (&v)[16], int t, const C* tw, X& xb) {
-    using P = Plan<N>;
-    if (N == 16) {
-        fft_stage<N, 16, 1, false, false, false>(v, t, tw, xb);
+template <int N, int VPT, bool TWT = false, typename C, typename X>
+__device__ __forceinline__ void fft_forward_v(C (&v)[VPT], int t, const C* tw, X& xb) {
+    using P = PlanV<N, VPT>;
+    if (N == VPT) {
+        fft_stage_v<N, VPT, VPT, 1, false, false, false, TWT>(v, t, tw, xb);
     } else {
-        fft_stage<N, 16, 1, false, false, true>(v, t, tw, xb);
+        fft_stage_v<N, VPT, VPT, 1, false, false, true, TWT>(v, t, tw, xb);
         if (P::R2 == 1) {
-            fft_stage<N, P::R1, 16, false, true, false>(v, t, tw, xb);
+            fft_stage_v<N, VPT, P::R1, VPT, false, true, false, TWT>(v, t, tw, xb);
         } else {
-            fft_stage<N, P::R1, 16, false, true, true>(v, t, tw, xb);
-            fft_stage<N, (P::R2 > 1 ? P::R2 : 2), 16 * P::R1, false, true, false>(v, t, tw, xb);
+            fft_stage_v<N, VPT, P::R1, VPT, false, true, true, TWT>(v, t, tw, xb);
+            fft_stage_v<N, VPT, (P::R2 > 1 ? P::R2 : 2), VPT * P::R1, false, true, false>(v, t, tw, xb);
         }
     }
 }
 
-template <int N, typename C, typename X>
-__device__ __forceinline__ void fft_inverse(C (&v)[16], int t, const C* tw, X& xb) {
-    using P = Plan<N>;
-    if (N == 16) {
-        fft_stage<N, 16, 1, true, false, false>(v, t, tw, xb);
+template <int N, int VPT, bool TWT = false, typename C, typename X>
+__device__ __forceinline__ void fft_inverse_v(C (&v)[VPT], int t, const C* tw, X& xb) {
+    using P = PlanV<N, VPT>;
+    if (N == VPT) {
+        fft_stage_v<N, VPT, VPT, 1, true, false, false, TWT>(v, t, tw, xb);
     } else if (P::R2 == 1) {
-        fft_stage<N, P::R1, 1, true, false, true>(v, t, tw, xb);
-        fft_stage<N, 16, P::R1, true, true, false>(v, t, tw, xb);
+        fft_stage_v<N, VPT, P::R1, 1, true, false, true, TWT>(v, t, tw, xb);
+        fft_stage_v<N, VPT, VPT, P::R1, true, true, false, TWT>(v, t, tw, xb);
     } else {
         constexpr int R2 = (P::R2 > 1 ? P::R2 : 2);
-        fft_stage<N, R2, 1, true, false, true>(v, t, tw, xb);
-        fft_stage<N, P::R1, R2, true, true, true>(v, t, tw, xb);
-        fft_stage<N, 16, R2 * P::R1, true, true, false>(v, t, tw, xb);
+        fft_stage_v<N, VPT, R2, 1, true, false, true, TWT>(v, t, tw, xb);
+        fft_stage_v<N, VPT, P::R1, R2, true, true, true, TWT>(v, t, tw, xb);
+        fft_stage_v<N, VPT, VPT, R2 * P::R1, true, true, false, TWT>(v, t, tw, xb);
     }
 }
+
+// 16 values per thread (the default plan)
+template <int N> __device__ __forceinline__ int spec_index(int t, int q) { return spec_index_v<N, 16>(t, q); }
+template <int N> __device__ __forceinline__ int line_index(int t, int q) { return line_index_v<N, 16>(t, q); }
+template <int N, typename C, typename X>
+__device__ __forceinline__ void fft_forward(C (&v)[16], int t, const C* tw, X& xb) { fft_forward_v<N, 16>(v, t, tw, xb); }
+template <int N, typename C, typename X>
+__device__ __forceinline__ void fft_inverse(C (&v)[16], int t, const C* tw, X& xb) { fft_inverse_v<N, 16>(v, t, tw, xb); }
 
 // Exchange policies ---------------------------------------------------------------
 // Contiguous lines (z axis): threads of a line are adjacent lanes; one line per
@@ -183,6 +199,16 @@ template <typename C, int N> struct XchgContig {
     __device__ __forceinline__ void st(int i, C v) const { base[i + (i >> 4)] = v; }
     __device__ __forceinline__ void sync() const {
         if (N / 16 <= 32) __syncwarp(); else __syncthreads();
+    }
+};
+// Same for the radix-8 plan: one pad element per 8 keeps the radix-8 scatter (8t + m) conflict free.
+template <typename C, int N> struct XchgContig8 {
+    C* base;
+    static constexpr int LS = N + N / 8;
+    __device__ __forceinline__ C ld(int i) const { return base[i + (i >> 3)]; }
+    __device__ __forceinline__ void st(int i, C v) const { base[i + (i >> 3)] = v; }
+    __device__ __forceinline__ void sync() const {
+        if (N / 8 <= 32) __syncwarp(); else __syncthreads();
     }
 };
 // Contiguous lines without padding: element i lives at i ^ ((i >> 4) & 15), which keeps both

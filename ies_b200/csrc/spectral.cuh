@@ -48,48 +48,64 @@ __device__ __forceinline__ void load_tables(C* tw, C* ml, const C* twg, const C*
 }
 
 // ---------------------------------------------------------------- z lines -----
-template <int N> struct ZCfg {
-    static constexpr int TT = N / 16;
+template <int N, int VPT> struct ZCfg {
+    static constexpr int TT = N / VPT;
     static constexpr int LPB = (256 / TT) > 0 ? (256 / TT) : 1;   // lines per block
     static constexpr int THREADS = LPB * TT;
 };
+template <typename C, int N, int VPT> struct ZXchg { using type = XchgContig<C, N>; };
+template <typename C, int N> struct ZXchg<C, N, 8> { using type = XchgContig8<C, N>; };
 
 // One CTA = LPB adjacent z lines.  Input lines start at line0 (+ blockIdx.x*LPB), the
-// derivative lines go to oline0 (+ blockIdx.x*LPB) of the scratch arrays.
-template <typename T, bool CPLX, int N>
-__global__ void __launch_bounds__(ZCfg<N>::THREADS)
+// derivative lines go to oline0 (+ blockIdx.x*LPB) of the scratch arrays.  VPT = register
+// values per thread (16: fewer, fatter threads; 8: twice the warps at half the registers).
+template <typename T, bool CPLX, int N, int VPT>
+__global__ void __launch_bounds__(ZCfg<N, VPT>::THREADS, (VPT == 8 ? 3 : 2))
 k_zline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict__ dA,
         void* __restrict__ dB, long line0, long oline0, long nlines,
         const typename Cx<T>::type* __restrict__ twg, const typename Cx<T>::type* __restrict__ mlg) {
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
+    using X = typename ZXchg<C, N, VPT>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* tw = reinterpret_cast<C*>(smem_raw);
     C* ml = tw + N;
     C* xbuf = ml + N;
-    load_tables(tw, ml, twg, mlg, N);
-    constexpr int TT = ZCfg<N>::TT, LPB = ZCfg<N>::LPB;
+    // N = VPT*VPT: both twiddled stages use W_N^(jj*m), jj, m < VPT; the table is laid out
+    // [m][jj] so that the threads of a line read consecutive entries (the master table's
+    // stride-m access costs 2.1x the wavefronts).
+    constexpr bool TWT = (N == VPT * VPT);
+    if constexpr (TWT) {
+        for (int q = threadIdx.x; q < N; q += blockDim.x) {
+            tw[q] = twg[((q / VPT) * (q % VPT)) & (N - 1)];
+            ml[q] = mlg[q];
+        }
+        __syncthreads();
+    } else {
+        load_tables(tw, ml, twg, mlg, N);
+    }
+    constexpr int TT = ZCfg<N, VPT>::TT, LPB = ZCfg<N, VPT>::LPB;
     const int t = threadIdx.x % TT, l = threadIdx.x / TT;
     const long line = (long)blockIdx.x * LPB + l;
     const bool ok = line < nlines;
     const size_t ibase = (size_t)(line0 + line) * N;
     const size_t obase = (size_t)(oline0 + line) * N;
-    XchgContig<C, N> xb{xbuf + (size_t)l * XchgContig<C, N>::LS};
+    X xb{xbuf + (size_t)l * X::LS};
 #pragma unroll 1
     for (int f = 0; f < F::NF; ++f) {
-        C v[16];
+        C v[VPT];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            if (ok) v[q] = F::ld(A, B, ibase + line_index<N>(t, q), f);
+        for (int q = 0; q < VPT; ++q) {
+            if (ok) v[q] = F::ld(A, B, ibase + line_index_v<N, VPT>(t, q), f);
             else { v[q].x = 0; v[q].y = 0; }
         }
-        fft_forward<N>(v, t, tw, xb);
+        fft_forward_v<N, VPT, TWT>(v, t, tw, xb);
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], ml[spec_index<N>(t, q)]);
-        fft_inverse<N>(v, t, tw, xb);
+        for (int q = 0; q < VPT; ++q) v[q] = cmul(v[q], ml[spec_index_v<N, VPT>(t, q)]);
+        fft_inverse_v<N, VPT, TWT>(v, t, tw, xb);
         if (ok) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) F::st(dA, dB, obase + line_index<N>(t, q), v[q], f);
+            for (int q = 0; q < VPT; ++q) F::st(dA, dB, obase + line_index_v<N, VPT>(t, q), v[q], f);
         }
     }
 }
@@ -143,7 +159,9 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 // ------------------------------------------ y lines + fused field update -----
 // Phase B of k_yline_update.  FAST: no CPML term touches the tile and every update box either
 // contains or misses it (upd = component mask, CTA-uniform): straight-line interior code.
-template <typename T, bool CPLX, int N, bool PAL, bool FAST>
+// SPLIT (SHPF): the z-line kernel has already updated G_y and left d/dz F_y in dz[0]; this
+// kernel updates G_x and G_z only (k_zline_update below).
+template <typename T, bool CPLX, int N, bool PAL, bool FAST, bool SPLIT>
 __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, const int k0, const unsigned mask,
                                               const int upd, const typename Cx<T>::type* xbuf) {
     using C = typename Cx<T>::type;
@@ -176,19 +194,28 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
             const int j = tr + (pass0 + u) * RP;
             const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
             VV::ld(p.dz[0], (size_t)((long long)idx + p.dz_off), dz0[u]);
-            VV::ld(p.dz[1], (size_t)((long long)idx + p.dz_off), dz1[u]);
-            if (p.pstd) {
-                VV::ld(p.dxs[0], idx, a3[u]);
-                VV::ld(p.dxs[1], idx, a4[u]);
-            } else if (nb_any) {
-                const size_t nidx = nbase + (size_t)j * p.nz + k;
-                VV::ld(nFz, nidx, a3[u]);
-                VV::ld(nFy, nidx, a4[u]);
-                VV::ld(p.F[2], idx, b3[u]);
-                VV::ld(p.F[1], idx, b4[u]);
-            }
+            if constexpr (SPLIT) {
+                if (nb_any) {
+                    VV::ld(nFy, nbase + (size_t)j * p.nz + k, a4[u]);
+                    VV::ld(p.F[1], idx, b4[u]);
+                }
+                VV::ld(p.G[0], idx, g[u][0]);
+                VV::ld(p.G[2], idx, g[u][2]);
+            } else {
+                VV::ld(p.dz[1], (size_t)((long long)idx + p.dz_off), dz1[u]);
+                if (p.pstd) {
+                    VV::ld(p.dxs[0], idx, a3[u]);
+                    VV::ld(p.dxs[1], idx, a4[u]);
+                } else if (nb_any) {
+                    const size_t nidx = nbase + (size_t)j * p.nz + k;
+                    VV::ld(nFz, nidx, a3[u]);
+                    VV::ld(nFy, nidx, a4[u]);
+                    VV::ld(p.F[2], idx, b3[u]);
+                    VV::ld(p.F[1], idx, b4[u]);
+                }
 #pragma unroll
-            for (int c = 0; c < 3; ++c) VV::ld(p.G[c], idx, g[u][c]);
+                for (int c = 0; c < 3; ++c) VV::ld(p.G[c], idx, g[u][c]);
+            }
             ld_coeff<V, PAL>(p, idx, cf[u]);
         }
 #pragma unroll
@@ -207,19 +234,33 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
                     d[0] = (double)r0.x; d[5] = (double)r0.y;
                 }
                 d[1] = dz0[u][v];
-                d[2] = dz1[u][v];
-                if (p.pstd) { d[3] = a3[u][v]; d[4] = a4[u][v]; }
-                else if (nb_any) {
-                    d[3] = a_scale(sx, a_sub(a3[u][v], b3[u][v]));
-                    d[4] = a_scale(sx, a_sub(a4[u][v], b4[u][v]));
-                } else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
-                A gg[3] = {g[u][0][v], g[u][1][v], g[u][2][v]};
-                if constexpr (FAST) cell_update_fast<CPLX>(upd, cf[u][v], d, gg);
-                else cell_update_regs<T, CPLX>(p, mask, i, j, k + v, cf[u][v], d, gg);
-                g[u][0][v] = gg[0]; g[u][1][v] = gg[1]; g[u][2][v] = gg[2];
+                if constexpr (SPLIT) {
+                    d[2] = a_zero(A()); d[3] = a_zero(A());
+                    d[4] = nb_any ? a_scale(sx, a_sub(a4[u][v], b4[u][v])) : a_zero(A());
+                    A gg[3] = {g[u][0][v], a_zero(A()), g[u][2][v]};
+                    if constexpr (FAST) cell_update_fast<CPLX, 5>(upd, cf[u][v], d, gg);
+                    else cell_update_regs<T, CPLX, 5>(p, mask, i, j, k + v, cf[u][v], d, gg);
+                    g[u][0][v] = gg[0]; g[u][2][v] = gg[2];
+                } else {
+                    d[2] = dz1[u][v];
+                    if (p.pstd) { d[3] = a3[u][v]; d[4] = a4[u][v]; }
+                    else if (nb_any) {
+                        d[3] = a_scale(sx, a_sub(a3[u][v], b3[u][v]));
+                        d[4] = a_scale(sx, a_sub(a4[u][v], b4[u][v]));
+                    } else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
+                    A gg[3] = {g[u][0][v], g[u][1][v], g[u][2][v]};
+                    if constexpr (FAST) cell_update_fast<CPLX>(upd, cf[u][v], d, gg);
+                    else cell_update_regs<T, CPLX>(p, mask, i, j, k + v, cf[u][v], d, gg);
+                    g[u][0][v] = gg[0]; g[u][1][v] = gg[1]; g[u][2][v] = gg[2];
+                }
             }
+            if constexpr (SPLIT) {
+                VV::st(p.G[0], idx, g[u][0]);
+                VV::st(p.G[2], idx, g[u][2]);
+            } else {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) VV::st(p.G[c], idx, g[u][c]);
+                for (int c = 0; c < 3; ++c) VV::st(p.G[c], idx, g[u][c]);
+            }
         }
     }
 }
@@ -232,7 +273,7 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
 //          enough bytes are in flight to cover HBM latency.
 // One CTA = the tile (plane i, columns kb*W .. kb*W+W-1, all rows).  PAL: coefficients come
 // from the palette form (update_dev.cuh ld_coeff).
-template <typename T, bool CPLX, int N, bool PAL>
+template <typename T, bool CPLX, int N, bool PAL, bool SPLIT>
 __global__ void __launch_bounds__(256, (CPLX ? 1 : 2))
 k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
                const typename Cx<T>::type* __restrict__ ml) {
@@ -281,8 +322,8 @@ k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
     // ---------------- phase B: vectorised streaming update ----------------
     const unsigned mask = term_mask(p, i, i + 1, 0, p.ny, k0, k0 + W);
     const int upd = tile_update_class(p, i, i + 1, 0, p.ny, k0, min(k0 + W, p.nz));
-    if (mask == 0u && upd >= 0) yline_phase_b<T, CPLX, N, PAL, true>(p, i, k0, mask, upd, xbuf);
-    else yline_phase_b<T, CPLX, N, PAL, false>(p, i, k0, mask, upd, xbuf);
+    if (mask == 0u && upd >= 0) yline_phase_b<T, CPLX, N, PAL, true, SPLIT>(p, i, k0, mask, upd, xbuf);
+    else yline_phase_b<T, CPLX, N, PAL, false, SPLIT>(p, i, k0, mask, upd, xbuf);
 }
 
 // ------------------------------------------------------------- launchers -----
@@ -314,19 +355,21 @@ int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
     const long line0 = (long)i0 * c->cfg.ny;
     const long oline0 = (long)out_i0 * c->cfg.ny;
     if (nlines <= 0) return 0;
-#define Z_CASE(NN) {                                                                        \
-        constexpr int LPB = ZCfg<NN>::LPB;                                                  \
-        size_t sm = sizeof(C) * (2 * NN + (size_t)LPB * XchgContig<C, NN>::LS);             \
-        auto kern = k_zline<T, CPLX, NN>;                                                   \
+#define Z_LAUNCH(NN, VV) {                                                                  \
+        constexpr int LPB = ZCfg<NN, VV>::LPB;                                              \
+        size_t sm = sizeof(C) * (2 * NN + (size_t)LPB * ZXchg<C, NN, VV>::type::LS);        \
+        auto kern = k_zline<T, CPLX, NN, VV>;                                               \
         if (set_smem(kern, sm)) return 1;                                                   \
         unsigned grid = (unsigned)((nlines + LPB - 1) / LPB);                               \
-        kern<<<grid, ZCfg<NN>::THREADS, sm, st>>>(A, B, dA, dB, line0, oline0, nlines,       \
+        kern<<<grid, ZCfg<NN, VV>::THREADS, sm, st>>>(A, B, dA, dB, line0, oline0, nlines,   \
             (const C*)c->tw[2], (const C*)c->mult[half][2]);                                \
     }
+#define Z_CASE(NN) Z_LAUNCH(NN, 16)       // 8 values per thread measured 54 % slower (more exchanges)
     if (st == c->stream) prof_mark(c, PROF_ZLINE, 0);
     IES_FOR_N(n, Z_CASE)
     if (st == c->stream) prof_mark(c, PROF_ZLINE, 1);
 #undef Z_CASE
+#undef Z_LAUNCH
     count_launch();
     IES_CUDA(cudaGetLastError());
     return 0;
@@ -368,7 +411,7 @@ int launch_sline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
 }
 
 template <typename T, bool CPLX>
-int launch_yline_update(Ctx* c, const UpdParams& p, int half) {
+int launch_yline_update(Ctx* c, const UpdParams& p, int half, bool split) {
     using C = typename Cx<T>::type;
     const int n = c->cfg.ny;
     if (p.i1 <= p.i0) return 0;
@@ -376,7 +419,8 @@ int launch_yline_update(Ctx* c, const UpdParams& p, int half) {
 #define Y_CASE(NN) {                                                                        \
         using S = SCfg<T, CPLX, NN>;                                                        \
         size_t sm = sizeof(C) * ((size_t)NN * S::W * Fld<T, CPLX>::NF);                     \
-        auto kern = pal ? k_yline_update<T, CPLX, NN, true> : k_yline_update<T, CPLX, NN, false>; \
+        auto kern = split ? (pal ? k_yline_update<T, CPLX, NN, true, true> : k_yline_update<T, CPLX, NN, false, true>) \
+                          : (pal ? k_yline_update<T, CPLX, NN, true, false> : k_yline_update<T, CPLX, NN, false, false>); \
         if (set_smem(kern, sm)) return 1;                                                   \
         dim3 grid((unsigned)((c->cfg.nz + S::W - 1) / S::W), (unsigned)(p.i1 - p.i0));      \
         kern<<<grid, S::THREADS, sm, c->stream>>>(p, (const C*)c->tw[1],                     \

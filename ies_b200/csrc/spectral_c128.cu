@@ -1,8 +1,8 @@
 // Explicit instantiation of the spectral kernels for field dtype c128.
-#include "shpf_half.cuh"
+#include "shpf_split.cuh"
 namespace ies {
 template int launch_zline<double, true>(Ctx*, const void*, const void*, void*, void*, int, int, int, int, cudaStream_t);
 template int launch_sline<double, true>(Ctx*, const void*, const void*, void*, void*, int, int, int, int);
-template int launch_shpf_half<double, true>(Ctx*, const UpdParams&, int);
-template int launch_yline_update<double, true>(Ctx*, const UpdParams&, int);
+template int launch_zline_update<double, true>(Ctx*, const UpdParams&, int);
+template int launch_yline_update<double, true>(Ctx*, const UpdParams&, int, bool);
 }  // namespace ies

@@ -127,7 +127,10 @@ template <int V, bool PAL> __device__ __forceinline__ void ld_coeff(const UpdPar
 //   comp x: d[0]-d[1]   comp y: d[2]-d[3]   comp z: d[4]-d[5]
 // A CPML term on component c always consumes one of that component's own two curl
 // derivatives (space.py:1153-1162 etc.), selected by the parity of its slot.
-template <typename T, bool CPLX>
+// COMPS: compile-time mask of the components this kernel updates (the split SHPF half-step
+// updates G_y in the z-line kernel and G_x, G_z in the y-line kernel); d[] / g[] entries of
+// the other components are not touched.
+template <typename T, bool CPLX, int COMPS = 7>
 __device__ __forceinline__ void cell_update_regs(const UpdParams& p, unsigned mask, int i, int j, int k,
                                                  const double C, const typename AccT<CPLX>::type (&d)[6],
                                                  typename AccT<CPLX>::type (&g)[3]) {
@@ -135,6 +138,7 @@ __device__ __forceinline__ void cell_update_regs(const UpdParams& p, unsigned ma
     using E = Elem<T, CPLX>;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+        if (!(COMPS & (1 << c))) continue;
         const A da = d[2 * c], db = d[2 * c + 1];
         if (in_box(p.box[c].lo, p.box[c].hi, i, j, k))
             g[c] = a_add(g[c], a_scale(C, a_sub(da, db)));
@@ -181,17 +185,18 @@ __device__ __forceinline__ int tile_update_class(const UpdParams& p, int i0, int
 // Interior fast path of cell_update_regs: no CPML term touches the tile and the update boxes
 // were resolved per tile (upd = tile_update_class(...) >= 0, CTA-uniform).  Same expression
 // as the general path, so both give identical bits.
-template <bool CPLX>
+template <bool CPLX, int COMPS = 7>
 __device__ __forceinline__ void cell_update_fast(const int upd, const double C,
                                                  const typename AccT<CPLX>::type (&d)[6],
                                                  typename AccT<CPLX>::type (&g)[3]) {
-    if (upd == 7) {
+    if ((upd & COMPS) == COMPS) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) g[c] = a_add(g[c], a_scale(C, a_sub(d[2 * c], d[2 * c + 1])));
+        for (int c = 0; c < 3; ++c)
+            if (COMPS & (1 << c)) g[c] = a_add(g[c], a_scale(C, a_sub(d[2 * c], d[2 * c + 1])));
     } else {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-            if (upd & (1 << c)) g[c] = a_add(g[c], a_scale(C, a_sub(d[2 * c], d[2 * c + 1])));
+            if ((COMPS & (1 << c)) && (upd & (1 << c))) g[c] = a_add(g[c], a_scale(C, a_sub(d[2 * c], d[2 * c + 1])));
     }
 }
 

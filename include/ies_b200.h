@@ -74,10 +74,10 @@ int ies_destroy(ies_ctx* ctx);
 int ies_set_stream(ies_ctx* ctx, void* cuda_stream);
 int ies_sync(ies_ctx* ctx);
 /* Engine tuning knobs (no reference counterpart; defaults need no call).  Names:
- * "alt" (1 = one alternating-orientation kernel per SHPF half-step, 0 = z-line + y-line
- * kernel pair), "palette" (1 = palette-compressed coefficient arrays when they hold
- * <= 256 distinct values), "prefetch" (1 = CTAs prefetch their streaming operands into L2),
- * "reset_psi" (zero the CPML auxiliary arrays). */
+ * "split" (1 = SHPF cell update split between the z-line and the y-line kernel [default],
+ * 0 = z-line derivative kernel + full y-line update kernel), "palette" (1 = palette-compressed coefficient arrays
+ * when they hold <= 32 distinct values; default 0), "reset_psi" (zero the CPML auxiliary
+ * arrays). */
 int ies_set_option(ies_ctx* ctx, const char* name, int64_t value);
 
 /* ---- setup --------------------------------------------------------------- */

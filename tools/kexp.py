@@ -22,13 +22,13 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 VARIANTS = [
-    ('base', dict(alt=0, palette=1)),
-    ('base_nopal', dict(alt=0, palette=0)),
-    ('alt', dict(alt=1, palette=1)),
-    ('alt_nopal', dict(alt=1, palette=0)),
+    ('base', dict(split=0, palette=0)),
+    ('base_pal', dict(split=0, palette=1)),
+    ('split', dict(split=1, palette=0)),
+    ('split_pal', dict(split=1, palette=1)),
 ]
-ALL_OPTS = ('alt', 'palette', 'prefetch')
-DEFAULTS = dict(alt=1, palette=0, prefetch=0)
+ALL_OPTS = ('split', 'palette')
+DEFAULTS = dict(split=0, palette=0)
 
 
 def main():
