@@ -174,6 +174,23 @@ __global__ void k_palette_index(const unsigned long long* __restrict__ cbits, si
     }
 }
 
+// One CTA per y-line tile (plane i, column block kb of w columns, all rows): writes the tile's
+// coefficient if every cell holds the same bit pattern, else a NaN.
+__global__ void k_tile_uniform(const unsigned long long* __restrict__ cbits, int ny, int nz, int w, double* __restrict__ out) {
+    const int i = blockIdx.y, kb = blockIdx.x;
+    const int k0 = kb * w, cols = min(w, nz - k0);
+    const size_t base = (size_t)i * ny * nz + k0;
+    const unsigned long long first = cbits[base];
+    int diff = 0;
+    for (int e = threadIdx.x; e < ny * cols; e += blockDim.x) {
+        const int j = e / cols, c = e - j * cols;
+        diff |= cbits[base + (size_t)j * nz + c] != first;
+    }
+    diff = __syncthreads_or(diff);
+    if (threadIdx.x == 0)
+        out[(size_t)i * gridDim.x + kb] = diff ? __longlong_as_double(0x7ff8000000000000LL) : __longlong_as_double((long long)first);
+}
+
 // pack / unpack a box for ies_get_field / ies_set_field
 template <typename S>
 __global__ void k_pack(const S* f, S* out, int ny, int nz, Box bx, int unpack) {
@@ -301,6 +318,7 @@ static int fill_params(ies_ctx* c, int half, UpdParams& p) {
     p.C = c->C[half];
     const bool pal = c->use_palette && c->Cnpal[half] > 0;
     p.Cidx = pal ? c->Cidx[half] : nullptr;
+    p.Ctile = (c->use_ctile && c->cfg.method != IES_FDTD) ? c->Ctile[half] : nullptr;
     for (int q = 0; q < MAX_PAL; ++q) p.cpal[q] = pal ? c->Cpal_host[half][q] : 0.0;
     if (!p.C) { set_error("init_update_constants() has not been called (no coefficients uploaded)"); return 1; }
     const bool nb = half == IES_HALF_H ? c->has_next : c->has_prev;
@@ -414,7 +432,9 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     const size_t ncell = (size_t)cfg->nx * cfg->ny * cfg->nz;
     const size_t fbytes = ncell * c->esize;
     for (int q = 0; q < 6; ++q) if (dev_alloc(c, &c->F[q], fbytes)) return 1;
-    for (int h = 0; h < 2; ++h) { c->C[h] = nullptr; c->Cidx[h] = nullptr; c->Cpal[h] = nullptr; c->Cnpal[h] = 0; }
+    for (int h = 0; h < 2; ++h) { c->C[h] = nullptr; c->Cidx[h] = nullptr; c->Cpal[h] = nullptr; c->Cnpal[h] = 0; c->Ctile[h] = nullptr; }
+    c->use_ctile = 1;
+    if (const char* e = getenv("IES_B200_CTILE")) c->use_ctile = atoi(e);
     c->use_palette = 0;     // measured slower than the f64 array (index -> value dependent loads), kept as an option
     if (const char* e = getenv("IES_B200_PALETTE")) c->use_palette = atoi(e);
     for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
@@ -474,6 +494,7 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     IES_CUDA(cudaSetDevice(c->cfg.device));
     IES_CUDA(cudaStreamSynchronize(c->stream));
     if (n == "palette") c->use_palette = v;
+    else if (n == "ctile") c->use_ctile = v;
     else if (n == "split") c->use_split = v;
     else if (n == "reset_psi") {               // zero the CPML auxiliary state (restart a run on new fields)
         for (int h = 0; h < 2; ++h)
@@ -532,6 +553,16 @@ int ies_set_coeff(ies_ctx* c, int half, const double* host, int64_t n) {
     IES_CUDA(cudaMemcpyAsync(c->C[half], host, ncell * 8, cudaMemcpyHostToDevice, c->stream));
     // palette form: materials are piecewise constant, so the array usually holds a handful of
     // distinct values; the update kernels then read one index byte per cell instead of 8 bytes
+    if (c->cfg.method != IES_FDTD) {
+        // per-tile uniform coefficients for the y-line kernel (tile = 4096/ny columns of one plane)
+        const int w = 4096 / c->cfg.ny > 0 ? 4096 / c->cfg.ny : 1;
+        const int kt = (c->cfg.nz + w - 1) / w;
+        if (!c->Ctile[half]) { void* p; if (dev_alloc(c, &p, (size_t)c->cfg.nx * kt * 8, false)) return 1; c->Ctile[half] = (double*)p; }
+        k_tile_uniform<<<dim3((unsigned)kt, (unsigned)c->cfg.nx), 256, 0, c->stream>>>(
+            (const unsigned long long*)c->C[half], c->cfg.ny, c->cfg.nz, w, c->Ctile[half]);
+        count_launch();
+        IES_CUDA(cudaGetLastError());
+    }
     c->Cnpal[half] = 0;
     if (!c->use_palette) return 0;
     if (!c->Cidx[half]) {

@@ -33,6 +33,7 @@ struct UpdParams {
     const uint8_t* Cidx;        // lossless palette form of C (<= MAX_PAL distinct values) or null:
     double cpal[MAX_PAL];       //   C[i] == cpal[Cidx[i]] bit for bit; 1 B/cell of HBM traffic instead of 8,
                                 //   the palette itself sits in the kernel-parameter constant bank
+    const double* Ctile;        // per y-line tile (plane, column block): the tile's one coefficient value, NaN if not uniform; or null
     const void* halo[2];        // neighbour planes of F_y, F_z (or null)
     const void* dz[2];          // scratch: d/dz F_y, d/dz F_x   (spectral methods)
     const void* dxs[2];         // scratch: d/dx F_z, d/dx F_y   (PSTD)
@@ -59,6 +60,8 @@ struct Ctx {
     double Cpal_host[2][MAX_PAL];
     int Cnpal[2];
     int use_palette;
+    double* Ctile[2];           // per-tile uniform coefficient of the y-line kernel's tiles (or null)
+    int use_ctile;
     void* scratch[4];           // dzA dzB dxA dxB
     void* halo_recv[2][2];
     void* mult[2][3];           // [half][axis] complex table in FFT precision, pre-scaled by 1/N

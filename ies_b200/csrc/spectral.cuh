@@ -161,9 +161,12 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 // contains or misses it (upd = component mask, CTA-uniform): straight-line interior code.
 // SPLIT (SHPF): the z-line kernel has already updated G_y and left d/dz F_y in dz[0]; this
 // kernel updates G_x and G_z only (k_zline_update below).
-template <typename T, bool CPLX, int N, bool PAL, bool FAST, bool SPLIT>
+// CM: where the coefficient comes from -- 0 the f64 array, 1 the palette form, 2 one value for
+// the whole tile (cuni; materials are piecewise constant, so most tiles are uniform and skip the
+// coefficient array altogether: one array pass less for the HBM-bound kernel).
+template <typename T, bool CPLX, int N, int CM, bool FAST, bool SPLIT>
 __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, const int k0, const unsigned mask,
-                                              const int upd, const typename Cx<T>::type* xbuf) {
+                                              const int upd, const typename Cx<T>::type* xbuf, const double cuni) {
     using C = typename Cx<T>::type;
     using A = typename AccT<CPLX>::type;
     using VV = Vec<T, CPLX>;
@@ -216,7 +219,12 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
 #pragma unroll
                 for (int c = 0; c < 3; ++c) VV::ld(p.G[c], idx, g[u][c]);
             }
-            ld_coeff<V, PAL>(p, idx, cf[u]);
+            if constexpr (CM == 2) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) cf[u][v] = cuni;
+            } else {
+                ld_coeff<V, CM == 1>(p, idx, cf[u]);
+            }
         }
 #pragma unroll
         for (int u = 0; u < PB; ++u) {
@@ -322,8 +330,12 @@ k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
     // ---------------- phase B: vectorised streaming update ----------------
     const unsigned mask = term_mask(p, i, i + 1, 0, p.ny, k0, k0 + W);
     const int upd = tile_update_class(p, i, i + 1, 0, p.ny, k0, min(k0 + W, p.nz));
-    if (mask == 0u && upd >= 0) yline_phase_b<T, CPLX, N, PAL, true, SPLIT>(p, i, k0, mask, upd, xbuf);
-    else yline_phase_b<T, CPLX, N, PAL, false, SPLIT>(p, i, k0, mask, upd, xbuf);
+    // per-tile uniform coefficient (engine.cu: k_tile_uniform), NaN when the tile is not uniform
+    const double cuni = p.Ctile ? p.Ctile[(size_t)i * gridDim.x + blockIdx.x] : __longlong_as_double(0x7ff8000000000000LL);
+    const bool fast = mask == 0u && upd >= 0;
+    if (fast && cuni == cuni) yline_phase_b<T, CPLX, N, 2, true, SPLIT>(p, i, k0, mask, upd, xbuf, cuni);
+    else if (fast) yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), true, SPLIT>(p, i, k0, mask, upd, xbuf, 0.0);
+    else yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), false, SPLIT>(p, i, k0, mask, upd, xbuf, 0.0);
 }
 
 // ------------------------------------------------------------- launchers -----

@@ -22,13 +22,12 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 VARIANTS = [
-    ('base', dict(split=0, palette=0)),
-    ('base_pal', dict(split=0, palette=1)),
-    ('split', dict(split=1, palette=0)),
-    ('split_pal', dict(split=1, palette=1)),
+    ('base', dict(split=0, ctile=0)),
+    ('ctile', dict(split=0, ctile=1)),
+    ('split_ctile', dict(split=1, ctile=1)),
 ]
-ALL_OPTS = ('split', 'palette')
-DEFAULTS = dict(split=0, palette=0)
+ALL_OPTS = ('split', 'palette', 'ctile')
+DEFAULTS = dict(split=0, palette=0, ctile=1)
 
 
 def main():
