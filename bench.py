@@ -267,7 +267,8 @@ def run_b200(args, rank, world, local_rank):
         return float(t.item())
 
     if world > 1:
-        sp._use_stream(torch.cuda.current_stream(local_rank).cuda_stream)
+        # engine and NCCL share comm's dedicated stream from the first step on
+        sp._use_stream(comm._stream_for(local_rank).cuda_stream)
 
     # ---------------- device-resident throughput (value) ----------------
     upload_all()

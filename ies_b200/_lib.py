@@ -67,6 +67,7 @@ SIGNATURES = {
     'ies_set_neighbours': (C.c_int, [_vp, C.c_int, C.c_int]),
     'ies_update_h': (C.c_int, [_vp, C.c_int64]),
     'ies_update_e': (C.c_int, [_vp, C.c_int64]),
+    'ies_update_phase': (C.c_int, [_vp, C.c_int, C.c_int]),
     'ies_halo_send_ptr': (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     'ies_halo_recv_ptr': (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     'ies_halo_copy': (C.c_int, [_vp, _vp, C.c_int]),

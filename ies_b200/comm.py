@@ -93,6 +93,7 @@ class TorchComm:
         self.rank = dist.get_rank(group)
         self.size = dist.get_world_size(group)
         self._views = {}
+        self._streams = {}
 
     def Get_rank(self): return self.rank
     def Get_size(self): return self.size
@@ -119,8 +120,9 @@ class TorchComm:
     def _tensors(self, space):
         import ctypes as C
         import torch
-        key = id(space)
-        if key not in self._views:
+        # cached on the space itself (an id()-keyed dict would hand a new space the views of a
+        # freed one that happened to get the same id)
+        if getattr(space, '_halo_views', None) is None:
             lib = _lib.load()
             dev = torch.device('cuda', space.device)
             v = {}
@@ -132,15 +134,49 @@ class TorchComm:
                         _lib.check(fn(space._ctx, half, w, C.byref(p), C.byref(n)))
                         ts.append(torch.as_tensor(_DevPlane(p.value, n.value), device=dev))
                     v[(half, kind)] = ts
-            self._views[key] = v
-        return self._views[key]
+            space._halo_views = v
+        return space._halo_views
+
+    def _stream_for(self, device):
+        """One dedicated (non-default) torch stream per device, shared by NCCL and the engine.
+        torch's default stream cannot be used: its handle is 0, which the C-ABI
+        (ies_set_stream) reads as "use the context's own stream" -- the kernels would then
+        run unordered against the NCCL transfers."""
+        import torch
+        if device not in self._streams:
+            dev = device[0] if isinstance(device, tuple) else device
+            self._streams[device] = torch.cuda.Stream(device=dev)
+        return self._streams[device]
 
     def exchange(self, space, half):
+        """In-order variant: transfer and kernels on one stream."""
         import torch
         v = self._tensors(space)
-        # run the engine on torch's current stream so NCCL and the kernels are ordered
-        space._use_stream(torch.cuda.current_stream(space.device).cuda_stream)
-        self.exchange_planes(half, v[(half, 'send')], v[(half, 'recv')])
+        st = self._stream_for(space.device)
+        space._use_stream(st.cuda_stream)          # engine kernels and NCCL on the same stream
+        with torch.cuda.stream(st):
+            self.exchange_planes(half, v[(half, 'send')], v[(half, 'recv')])
+
+    def exchange_begin(self, space, half):
+        """Overlapped variant: the NCCL send/recv runs on a second stream once the engine
+        stream has finished the previous update (event), and returns the event the
+        neighbour-dependent part of the half-step has to wait for."""
+        import torch
+        v = self._tensors(space)
+        se = self._stream_for(space.device)
+        sc = self._stream_for((space.device, 'comm'))
+        space._use_stream(se.cuda_stream)
+        ready = torch.cuda.Event()
+        ready.record(se)                           # fields of the previous half-step are final
+        sc.wait_event(ready)
+        with torch.cuda.stream(sc):
+            self.exchange_planes(half, v[(half, 'send')], v[(half, 'recv')])
+            done = torch.cuda.Event()
+            done.record(sc)
+        return done
+
+    def exchange_end(self, space, done):
+        self._stream_for(space.device).wait_event(done)
 
     def gather(self, arr, root=0):
         out = [None] * self.size if self.rank == root else None

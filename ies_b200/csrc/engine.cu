@@ -344,11 +344,15 @@ static int ensure_scratch(ies_ctx* c, int first, int last) {
     return 0;
 }
 
+// phase: -1 = whole half-step; 0 = the part that needs no neighbour plane (the z-line and
+// x-line derivative passes), so that a slab's halo exchange can overlap it; 1 = the rest.
 template <typename T, bool CP>
-static int do_update(ies_ctx* c, int half) {
+static int do_update(ies_ctx* c, int half, int phase) {
     UpdParams p;
     if (fill_params(c, half, p)) return 1;
     const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
+    const bool overlap_ok = c->cfg.method != IES_FDTD && !(c->cfg.method == IES_SHPF && c->use_split);
+    if (!overlap_ok) { if (phase == 0) return 0; phase = -1; }       // everything in phase 1
     if (c->cfg.method == IES_FDTD) {
         // ghost copies on the differentiated field, axis order x, y, z (space.py:1798-1858)
         for (int a = 0; a < 3; ++a) {
@@ -386,12 +390,16 @@ static int do_update(ies_ctx* c, int half) {
         return 0;
     }
     p.dxs[0] = c->scratch[2]; p.dxs[1] = c->scratch[3];
-    if (c->cfg.method == IES_PSTD) {
-        if (!c->mult[half][0]) { set_error("x multiplier not set"); return 1; }
-        if (launch_sline<T, CP>(c, p.F[2], p.F[1], c->scratch[2], c->scratch[3], half, 0, 0, nx)) return 1;
+    if (phase != 1) {
+        if (c->cfg.method == IES_PSTD) {
+            if (!c->mult[half][0]) { set_error("x multiplier not set"); return 1; }
+            if (launch_sline<T, CP>(c, p.F[2], p.F[1], c->scratch[2], c->scratch[3], half, 0, 0, nx)) return 1;
+        }
+        if (launch_zline<T, CP>(c, p.F[1], p.F[0], c->scratch[0], c->scratch[1], half, 0, nx, 0)) return 1;
     }
-    if (launch_zline<T, CP>(c, p.F[1], p.F[0], c->scratch[0], c->scratch[1], half, 0, nx, 0)) return 1;
-    if (launch_yline_update<T, CP>(c, p, half, false)) return 1;
+    if (phase != 0) {
+        if (launch_yline_update<T, CP>(c, p, half, false)) return 1;
+    }
     return 0;
 }
 
@@ -506,7 +514,14 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     return 0;
 }
 
-int ies_set_stream(ies_ctx* c, void* s) { c->stream = s ? (cudaStream_t)s : c->own_stream; return 0; }
+int ies_set_stream(ies_ctx* c, void* s) {
+    // work already queued on the old stream (set-up, a source injection) must be visible to
+    // whatever is enqueued on the new one
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    IES_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
 int ies_timer_start(ies_ctx* c) {
     IES_CUDA(cudaSetDevice(c->cfg.device));
     IES_CUDA(cudaEventRecord(c->ev_t0, c->stream));
@@ -663,12 +678,18 @@ int ies_set_neighbours(ies_ctx* c, int has_prev, int has_next) { c->has_prev = h
 
 int ies_update_h(ies_ctx* c, int64_t) {
     IES_CUDA(cudaSetDevice(c->cfg.device));
-    DISPATCH(c, return (do_update<T, CP>(c, IES_HALF_H)));
+    DISPATCH(c, return (do_update<T, CP>(c, IES_HALF_H, -1)));
     return 0;
 }
 int ies_update_e(ies_ctx* c, int64_t) {
     IES_CUDA(cudaSetDevice(c->cfg.device));
-    DISPATCH(c, return (do_update<T, CP>(c, IES_HALF_E)));
+    DISPATCH(c, return (do_update<T, CP>(c, IES_HALF_E, -1)));
+    return 0;
+}
+int ies_update_phase(ies_ctx* c, int half, int phase) {
+    if (half < 0 || half > 1 || phase < 0 || phase > 1) { set_error("ies_update_phase: bad half/phase"); return 1; }
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    DISPATCH(c, return (do_update<T, CP>(c, half, phase)));
     return 0;
 }
 

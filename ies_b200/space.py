@@ -623,14 +623,27 @@ class Basic3D:
     def updateH(self, tstep):
         """space.py:639-840: halo (Ey[0],Ez[0] from rank+1), derivatives, update, Bloch, CPML."""
         if self._dirty: self._finalize()
-        if self.MPIsize > 1: self.MPIcomm.exchange(self, _lib.HALF_H)
-        _lib.check(self._lib.ies_update_h(self._ctx, int(tstep)))
+        self._half_step(_lib.HALF_H, tstep)
 
     def updateE(self, tstep):
         """space.py:842-1052: halo (Hy[-1],Hz[-1] from rank-1), derivatives, update, Bloch, CPML."""
         if self._dirty: self._finalize()
-        if self.MPIsize > 1: self.MPIcomm.exchange(self, _lib.HALF_E)
-        _lib.check(self._lib.ies_update_e(self._ctx, int(tstep)))
+        self._half_step(_lib.HALF_E, tstep)
+
+    def _half_step(self, half, tstep):
+        """Halo exchange + update.  A comm with exchange_begin/exchange_end (TorchComm) runs the
+        transfer on its own stream while the engine does the part of the half-step that needs
+        no neighbour plane (the z-line derivative pass); the rest waits for the halo event."""
+        comm = self.MPIcomm
+        if self.MPIsize > 1 and hasattr(comm, 'exchange_begin'):
+            token = comm.exchange_begin(self, half)
+            _lib.check(self._lib.ies_update_phase(self._ctx, half, 0))
+            comm.exchange_end(self, token)
+            _lib.check(self._lib.ies_update_phase(self._ctx, half, 1))
+            return
+        if self.MPIsize > 1: comm.exchange(self, half)
+        fn = self._lib.ies_update_h if half == _lib.HALF_H else self._lib.ies_update_e
+        _lib.check(fn(self._ctx, int(tstep)))
 
 
 class Empty3D(Basic3D):

@@ -107,6 +107,10 @@ int ies_set_neighbours(ies_ctx* ctx, int has_prev, int has_next);
  * exchange: the halo planes must already be in the buffers of ies_halo_recv_ptr. */
 int ies_update_h(ies_ctx* ctx, int64_t tstep);
 int ies_update_e(ies_ctx* ctx, int64_t tstep);
+/* The same half-step in two parts, so that a slab's halo exchange (space.py:645-670, 863-887)
+ * can overlap the part that needs no neighbour plane: phase 0 = z-line / x-line derivative
+ * passes (nothing for FDTD), phase 1 = the rest.  phase 0 then phase 1 == ies_update_h/e. */
+int ies_update_phase(ies_ctx* ctx, int half, int phase);
 /* Device pointers for the halo exchange (space.py:645-670, 863-887).
  * half = IES_HALF_H: send = Ey[0], Ez[0] (to rank-1), recv = planes of rank+1;
  * half = IES_HALF_E: send = Hy[-1], Hz[-1] (to rank+1), recv = planes of rank-1.
