@@ -68,6 +68,87 @@ __global__ void __launch_bounds__(256) k_fdtd(const UpdParams p) {
     cell_update<T, CPLX, PAL>(p, mask, i, j, k, d);
 }
 
+// Vectorised variant: 16-byte accesses, V cells along z per thread, block = 32 z-vectors x 8
+// rows of one x-plane; the z neighbour of a vector is its own shifted lanes plus one scalar.
+// Blocks whose tile lies inside all three update boxes and touches no CPML term (FAST) run
+// straight-line code.  Needs nz % V == 0 (16-byte aligned rows); do_update falls back to k_fdtd.
+template <typename T, bool CPLX, bool PAL, bool FAST>
+__device__ __forceinline__ void fdtd_vec_body(const UpdParams& p, const unsigned mask, const int upd) {
+    using A = typename AccT<CPLX>::type;
+    using E = Elem<T, CPLX>;
+    using VV = Vec<T, CPLX>;
+    constexpr int V = VV::V;
+    const int k = (blockIdx.x * 32 + threadIdx.x) * V;
+    const int j = blockIdx.y * 8 + threadIdx.y;
+    const int i = p.i0 + blockIdx.z;
+    if (k >= p.nz || j >= p.ny) return;
+    const size_t plane = (size_t)p.ny * p.nz;
+    const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
+    const int dir = p.dir;
+    const double sy = dir > 0 ? p.rdy : -p.rdy, sz = dir > 0 ? p.rdz : -p.rdz, sx = dir > 0 ? p.rdx : -p.rdx;
+    A fx[V], fy[V], fz[V], g[3][V], ny_z[V], ny_x[V], nx_z[V], nx_y[V];
+    double cf[V];
+    VV::ld(p.F[0], idx, fx); VV::ld(p.F[1], idx, fy); VV::ld(p.F[2], idx, fz);
+    const int jn = j + dir, in = i + dir;
+    const bool has_y = jn >= 0 && jn < p.ny;
+    const bool x_in = in >= 0 && in < p.nx;
+    const bool has_x = x_in || p.halo[0] != nullptr;
+    if (has_y) {
+        const size_t n = idx + (ptrdiff_t)dir * p.nz;
+        VV::ld(p.F[2], n, ny_z); VV::ld(p.F[0], n, ny_x);
+    }
+    if (has_x) {
+        const size_t n = x_in ? idx + (ptrdiff_t)dir * plane : (size_t)j * p.nz + k;
+        VV::ld(x_in ? p.F[2] : p.halo[1], n, nx_z);
+        VV::ld(x_in ? p.F[1] : p.halo[0], n, nx_y);
+    }
+    // the one z neighbour outside the vector: element k+V (dir > 0) or k-1 (dir < 0)
+    const int ke = dir > 0 ? k + V : k - 1;
+    const bool has_ze = ke >= 0 && ke < p.nz;
+    A ez_y = a_zero(A()), ez_x = a_zero(A());
+    if (has_ze) {
+        const size_t n = (size_t)i * plane + (size_t)j * p.nz + ke;
+        ez_y = E::ld(p.F[1], n); ez_x = E::ld(p.F[0], n);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) VV::ld(p.G[c], idx, g[c]);
+    ld_coeff<V, PAL>(p, idx, cf);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        A d[6];
+        if (has_y) { d[0] = a_scale(sy, a_sub(ny_z[v], fz[v])); d[5] = a_scale(sy, a_sub(ny_x[v], fx[v])); }
+        else { d[0] = a_zero(A()); d[5] = a_zero(A()); }
+        // z neighbour: a lane of the same vector, or the extra element at its end
+        const A upy = (v + 1 < V) ? fy[(v + 1 < V) ? v + 1 : v] : ez_y, upx = (v + 1 < V) ? fx[(v + 1 < V) ? v + 1 : v] : ez_x;
+        const A dny = (v >= 1) ? fy[(v >= 1) ? v - 1 : v] : ez_y, dnx = (v >= 1) ? fx[(v >= 1) ? v - 1 : v] : ez_x;
+        const bool zok = dir > 0 ? ((v + 1 < V) || has_ze) : ((v >= 1) || has_ze);
+        if (zok) {
+            const A zy = dir > 0 ? upy : dny, zx = dir > 0 ? upx : dnx;
+            d[1] = a_scale(sz, a_sub(zy, fy[v])); d[2] = a_scale(sz, a_sub(zx, fx[v]));
+        } else { d[1] = a_zero(A()); d[2] = a_zero(A()); }
+        if (has_x) { d[3] = a_scale(sx, a_sub(nx_z[v], fz[v])); d[4] = a_scale(sx, a_sub(nx_y[v], fy[v])); }
+        else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
+        A gg[3] = {g[0][v], g[1][v], g[2][v]};
+        if constexpr (FAST) cell_update_fast<CPLX>(upd, cf[v], d, gg);
+        else cell_update_regs<T, CPLX>(p, mask, i, j, k + v, cf[v], d, gg);
+        g[0][v] = gg[0]; g[1][v] = gg[1]; g[2][v] = gg[2];
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) VV::st(p.G[c], idx, g[c]);
+}
+
+template <typename T, bool CPLX, bool PAL>
+__global__ void __launch_bounds__(256) k_fdtd_vec(const UpdParams p) {
+    constexpr int V = Vec<T, CPLX>::V;
+    const int i = p.i0 + blockIdx.z;
+    const int j0 = blockIdx.y * 8, k0 = blockIdx.x * 32 * V;
+    const int j1 = min(j0 + 8, p.ny), k1 = min(k0 + 32 * V, p.nz);
+    const unsigned mask = term_mask(p, i, i + 1, j0, j1, k0, k1);
+    const int upd = tile_update_class(p, i, i + 1, j0, j1, k0, k1);
+    if (mask == 0u && upd >= 0) fdtd_vec_body<T, CPLX, PAL, true>(p, mask, upd);
+    else fdtd_vec_body<T, CPLX, PAL, false>(p, mask, upd);
+}
+
 // Ghost-plane copies F[-1] = F[1]*pp ; F[0] = F[-2]*pm along `axis` for the three
 // components, and for the two halo planes along y/z (space.py:1714-1796).
 template <typename T, bool CPLX>
@@ -369,11 +450,19 @@ static int do_update(ies_ctx* c, int half, int phase) {
                 make_double2(c->ghost_pm[a][0], c->ghost_pm[a][1]));
             count_launch();
         }
-        dim3 blk(nz >= 64 ? 64 : 32, nz >= 64 ? 4 : 8, 1);
-        dim3 grid((nz + blk.x - 1) / blk.x, (ny + blk.y - 1) / blk.y, nx);
+        constexpr int V = Vec<T, CP>::V;
         prof_mark(c, PROF_FDTD, 0);
-        if (p.Cidx) k_fdtd<T, CP, true><<<grid, blk, 0, c->stream>>>(p);
-        else k_fdtd<T, CP, false><<<grid, blk, 0, c->stream>>>(p);
+        if (c->fdtd_vec && nz % V == 0) {
+            dim3 blk(32, 8, 1);
+            dim3 grid((nz + 32 * V - 1) / (32 * V), (ny + 7) / 8, nx);
+            if (p.Cidx) k_fdtd_vec<T, CP, true><<<grid, blk, 0, c->stream>>>(p);
+            else k_fdtd_vec<T, CP, false><<<grid, blk, 0, c->stream>>>(p);
+        } else {
+            dim3 blk(nz >= 64 ? 64 : 32, nz >= 64 ? 4 : 8, 1);
+            dim3 grid((nz + blk.x - 1) / blk.x, (ny + blk.y - 1) / blk.y, nx);
+            if (p.Cidx) k_fdtd<T, CP, true><<<grid, blk, 0, c->stream>>>(p);
+            else k_fdtd<T, CP, false><<<grid, blk, 0, c->stream>>>(p);
+        }
         prof_mark(c, PROF_FDTD, 1);
         count_launch();
         IES_CUDA(cudaGetLastError());
@@ -442,6 +531,8 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     for (int q = 0; q < 6; ++q) if (dev_alloc(c, &c->F[q], fbytes)) return 1;
     for (int h = 0; h < 2; ++h) { c->C[h] = nullptr; c->Cidx[h] = nullptr; c->Cpal[h] = nullptr; c->Cnpal[h] = 0; c->Ctile[h] = nullptr; }
     c->use_ctile = 1;
+    c->fdtd_vec = 1;
+    if (const char* e = getenv("IES_B200_FDTD_VEC")) c->fdtd_vec = atoi(e);
     if (const char* e = getenv("IES_B200_CTILE")) c->use_ctile = atoi(e);
     c->use_palette = 0;     // measured slower than the f64 array (index -> value dependent loads), kept as an option
     if (const char* e = getenv("IES_B200_PALETTE")) c->use_palette = atoi(e);
@@ -503,6 +594,7 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     IES_CUDA(cudaStreamSynchronize(c->stream));
     if (n == "palette") c->use_palette = v;
     else if (n == "ctile") c->use_ctile = v;
+    else if (n == "fdtd_vec") c->fdtd_vec = v;
     else if (n == "split") c->use_split = v;
     else if (n == "reset_psi") {               // zero the CPML auxiliary state (restart a run on new fields)
         for (int h = 0; h < 2; ++h)

@@ -62,6 +62,7 @@ struct Ctx {
     int use_palette;
     double* Ctile[2];           // per-tile uniform coefficient of the y-line kernel's tiles (or null)
     int use_ctile;
+    int fdtd_vec;               // FDTD: 16-byte vectorised kernel when nz allows (k_fdtd_vec)
     void* scratch[4];           // dzA dzB dxA dxB
     void* halo_recv[2][2];
     void* mult[2][3];           // [half][axis] complex table in FFT precision, pre-scaled by 1/N

@@ -54,3 +54,55 @@ def test_split_update_matches_unsplit_update(product, name, monkeypatch):
     b = H.run_product(product, case)
     for n in C.FIELDS:
         assert np.array_equal(np.asarray(a[n]), np.asarray(b[n])), n
+
+
+def _run_with_env(product, case, monkeypatch, **env):
+    for k, v in env.items():
+        monkeypatch.setenv(k, str(v))
+    return H.run_product(product, case)
+
+
+@pytest.mark.parametrize('name', ['fdtd_f64_xpml_pbc', 'fdtd_c64_xpml_pbc', 'fdtd_c128_bloch_yz', 'fdtd_f64_allpml',
+                                  'fdtd_f64_allpml_r2', 'fdtd_c128_pbcx'])
+def test_fdtd_vector_kernel_matches_scalar_kernel(product, name, monkeypatch):
+    """k_fdtd_vec (16-byte accesses, tile-level fast path) and the one-thread-per-cell k_fdtd
+    compute bit-identical fields."""
+    case = C.CASES_BY_NAME[name]
+    a = _run_with_env(product, case, monkeypatch, IES_B200_FDTD_VEC=1)
+    b = _run_with_env(product, case, monkeypatch, IES_B200_FDTD_VEC=0)
+    for n in C.FIELDS:
+        assert np.array_equal(np.asarray(a[n]), np.asarray(b[n])), n
+
+
+@pytest.mark.parametrize('name', ['shpf_f64_xpml', 'shpf_f64_allpml_r2', 'shpf_c128_bloch_yz', 'shpf_f64_xpml_64',
+                                  'pstd_f64_allpml', 'pstd_c128_bloch_all'])
+def test_uniform_tile_coefficients_match_array(product, name, monkeypatch):
+    """Tiles whose coefficient is uniform skip the coefficient array (k_tile_uniform): same bits."""
+    case = C.CASES_BY_NAME[name]
+    a = _run_with_env(product, case, monkeypatch, IES_B200_CTILE=1)
+    b = _run_with_env(product, case, monkeypatch, IES_B200_CTILE=0)
+    for n in C.FIELDS:
+        assert np.array_equal(np.asarray(a[n]), np.asarray(b[n])), n
+
+
+@pytest.mark.parametrize('name', ['shpf_f64_xpml_64', 'fdtd_f64_xpml_pbc', 'pstd_f64_allpml'])
+def test_two_phase_half_step_equals_whole_half_step(product, name):
+    """ies_update_phase(half, 0) + ies_update_phase(half, 1) == ies_update_h / ies_update_e."""
+    from ies_b200 import _lib
+    lib = _lib.load()
+    case = C.CASES_BY_NAME[name]
+    out = []
+    for phased in (False, True):
+        sp, setter = C.build_api(product, case, 'b200')
+        for t in range(case['steps']):
+            setter.put_src(case['src_field'], C.pulse_value(case, t, sp.dt), case['put'])
+            if phased:
+                if sp._dirty: sp._finalize()
+                for half in (_lib.HALF_H, _lib.HALF_E):
+                    _lib.check(lib.ies_update_phase(sp._ctx, half, 0))
+                    _lib.check(lib.ies_update_phase(sp._ctx, half, 1))
+            else:
+                sp.updateH(t); sp.updateE(t)
+        out.append({n: np.asarray(getattr(sp, n)[:, :, :]) for n in C.FIELDS})
+    for n in C.FIELDS:
+        assert np.array_equal(out[0][n], out[1][n]), n
