@@ -291,30 +291,40 @@ struct DftDev {
     long ncell;
 };
 
-// phase[f] = exp(2 pi i f t dt) * dt with the operand order of collector.py:334
-__global__ void k_dft_phase(const double* freqs, int nf, double tstep, double dt, double2* phase) {
+// Running DFT of the collectors, time-blocked: do_RFT only SAMPLES the four tangential
+// components on the plane into a ring of DFT_TB time slots (2 array passes over the plane);
+// every DFT_TB steps (or when a result is read) k_dft_acc_block adds the slots to the
+// accumulators in time order -- the (Nf, plane) complex accumulators, the dominant traffic of
+// collector.py:323-338 (4 x Nf x plane x 32 B per step), are read and written once per block.
+// The per-step arithmetic (operand order of collector.py:334) and the summation order are
+// unchanged, so the spectra are bit-identical to a step-by-step accumulation.
+constexpr int DFT_TB = 16;
+struct DftTimes { double t[DFT_TB]; };
+
+// phase[s][f] = exp(2 pi i f t_s dt)
+__global__ void k_dft_phase(const double* freqs, int nf, DftTimes ts, int nslots, double dt, double2* phase) {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= nf) return;
-    const double arg = ((2.0 * 3.141592653589793) * freqs[f]) * tstep * dt;
-    double s, c;
-    sincos(arg, &s, &c);
-    phase[f] = make_double2(c, s);
+    const int s = blockIdx.y;
+    if (f >= nf || s >= nslots) return;
+    const double arg = ((2.0 * 3.141592653589793) * freqs[f]) * ts.t[s] * dt;
+    double sn, cs;
+    sincos(arg, &sn, &cs);
+    phase[(size_t)s * nf + f] = make_double2(cs, sn);
 }
 
+// ring[(slot*4 + q) * ncell + cell] = component q on the collector plane (SF = TF - IF lazily)
 template <typename T, bool CPLX>
 __global__ void __launch_bounds__(256)
-k_dft_acc(DftDev d, const void* a0, const void* a1, const void* a2, const void* a3,
-          const void* b0, const void* b1, const void* b2, const void* b3,
-          int ny, int nz, Box bx, const double2* __restrict__ phase, double dt) {
+k_dft_sample(double2* __restrict__ ring, long ncell, int slot, const void* a0, const void* a1, const void* a2,
+             const void* a3, const void* b0, const void* b1, const void* b2, const void* b3, int ny, int nz, Box bx) {
     using E = Elem<T, CPLX>;
     const int ey = bx.hi[1] - bx.lo[1], ez = bx.hi[2] - bx.lo[2];
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= d.ncell) return;
+    if (tid >= ncell) return;
     const int c = (int)(tid % ez), b = (int)((tid / ez) % ey), a = (int)(tid / ((long)ez * ey));
     const size_t idx = ((size_t)(bx.lo[0] + a) * ny + (bx.lo[1] + b)) * nz + (bx.lo[2] + c);
     const void* fa[4] = {a0, a1, a2, a3};
     const void* fb[4] = {b0, b1, b2, b3};
-    double2 v[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         auto x = E::ld(fa[q], idx);
@@ -322,21 +332,42 @@ k_dft_acc(DftDev d, const void* a0, const void* a1, const void* a2, const void* 
             // Empty3D.get_SF: SF = TF - IF, evaluated in field precision (space.py:2173-2179)
             x = E::rnd(a_sub(x, E::ld(fb[q], idx)));
         }
-        if constexpr (CPLX) v[q] = x; else v[q] = make_double2(x, 0.0);
+        double2 v;
+        if constexpr (CPLX) v = x; else v = make_double2(x, 0.0);
+        ring[((size_t)slot * 4 + q) * ncell + tid] = v;
     }
-    for (int f = 0; f < d.nf; ++f) {
-        const double2 ph = phase[f];
+}
+
+// One thread = one (component, cell): its nslots samples stay in registers while it walks the
+// frequencies; phase table [slot][f] in shared memory.
+template <bool CPLX>
+__global__ void __launch_bounds__(256)
+k_dft_acc_block(DftDev d, const double2* __restrict__ ring, const double2* __restrict__ phase, int nslots, double dt) {
+    extern __shared__ double2 sph[];
+    for (int e = threadIdx.x; e < nslots * d.nf; e += blockDim.x) sph[e] = phase[e];
+    __syncthreads();
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int q = blockIdx.y;
+    if (tid >= d.ncell) return;
+    double2 v[DFT_TB];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            double2* acc = d.acc[q] + (size_t)f * d.ncell + tid;
-            double2 s = *acc;
-            // (F * exp(..)) * dt
-            double re, im;
-            if constexpr (CPLX) { re = v[q].x * ph.x - v[q].y * ph.y; im = v[q].x * ph.y + v[q].y * ph.x; }
-            else { re = v[q].x * ph.x; im = v[q].x * ph.y; }
-            s.x += re * dt; s.y += im * dt;
-            *acc = s;
+    for (int s = 0; s < DFT_TB; ++s)
+        v[s] = s < nslots ? ring[((size_t)s * 4 + q) * d.ncell + tid] : make_double2(0.0, 0.0);
+    for (int f = 0; f < d.nf; ++f) {
+        double2* acc = d.acc[q] + (size_t)f * d.ncell + tid;
+        double2 sum = *acc;
+#pragma unroll
+        for (int s = 0; s < DFT_TB; ++s) {
+            if (s < nslots) {
+                const double2 ph = sph[s * d.nf + f];
+                // (F * exp(..)) * dt
+                double re, im;
+                if constexpr (CPLX) { re = v[s].x * ph.x - v[s].y * ph.y; im = v[s].x * ph.y + v[s].y * ph.x; }
+                else { re = v[s].x * ph.x; im = v[s].x * ph.y; }
+                sum.x += re * dt; sum.y += im * dt;
+            }
         }
+        *acc = sum;
     }
 }
 
@@ -368,7 +399,13 @@ struct ies_dft {
     long ncell;
     double2* acc[4];
     double* freqs;
-    double2* phase;
+    double2* phase;             // [DFT_TB][nf]
+    double2* ring;              // [DFT_TB][4][ncell] sampled plane values not yet accumulated
+    int npend;                  // filled slots
+    double pend_t[DFT_TB];      // their time steps
+    double dt;
+    bool cplx;
+    cudaStream_t last_stream;
 };
 struct ies_probe {
     ies_ctx* ctx;
@@ -932,10 +969,36 @@ int ies_dft_create(ies_ctx* c, const int32_t lo[3], const int32_t hi[3], const i
         IES_CUDA(cudaMemsetAsync(d->acc[q], 0, b, c->stream));
     }
     IES_CUDA(cudaMalloc((void**)&d->freqs, (size_t)nf * 8));
-    IES_CUDA(cudaMalloc((void**)&d->phase, (size_t)nf * 16));
+    IES_CUDA(cudaMalloc((void**)&d->phase, (size_t)DFT_TB * nf * 16));
+    IES_CUDA(cudaMalloc((void**)&d->ring, (size_t)DFT_TB * 4 * (d->ncell > 0 ? d->ncell : 1) * 16));
+    d->npend = 0; d->dt = c->cfg.dt; d->cplx = c->cplx; d->last_stream = c->stream;
     IES_CUDA(cudaMemcpyAsync(d->freqs, freqs, (size_t)nf * 8, cudaMemcpyHostToDevice, c->stream));
     IES_CUDA(cudaStreamSynchronize(c->stream));
     *out = d;
+    return 0;
+}
+
+// adds the pending time slots to the accumulators (stream order: after their sampling kernels)
+static int dft_flush(ies_dft* d) {
+    if (d->npend == 0 || d->ncell <= 0) { d->npend = 0; return 0; }
+    cudaStream_t st = d->last_stream;
+    DftTimes ts;
+    for (int s = 0; s < DFT_TB; ++s) ts.t[s] = s < d->npend ? d->pend_t[s] : 0.0;
+    k_dft_phase<<<dim3((d->nf + 127) / 128, d->npend), 128, 0, st>>>(d->freqs, d->nf, ts, d->npend, d->dt, d->phase);
+    DftDev dd; dd.nf = d->nf; dd.ncell = d->ncell;
+    for (int q = 0; q < 4; ++q) dd.acc[q] = d->acc[q];
+    const size_t sm = (size_t)d->npend * d->nf * 16;
+    const dim3 grid((unsigned)((d->ncell + 255) / 256), 4);
+    if (d->cplx) {
+        if (sm > 48 * 1024) IES_CUDA(cudaFuncSetAttribute(k_dft_acc_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_dft_acc_block<true><<<grid, 256, sm, st>>>(dd, d->ring, d->phase, d->npend, d->dt);
+    } else {
+        if (sm > 48 * 1024) IES_CUDA(cudaFuncSetAttribute(k_dft_acc_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        k_dft_acc_block<false><<<grid, 256, sm, st>>>(dd, d->ring, d->phase, d->npend, d->dt);
+    }
+    count_launch(2);
+    IES_CUDA(cudaGetLastError());
+    d->npend = 0;
     return 0;
 }
 
@@ -945,31 +1008,40 @@ int ies_dft_accumulate(ies_dft* d, ies_ctx* a, ies_ctx* b, int64_t tstep) {
     if (b && (b->cfg.dtype != a->cfg.dtype || b->cfg.nx != a->cfg.nx || b->cfg.ny != a->cfg.ny || b->cfg.nz != a->cfg.nz)) {
         set_error("get_SF: TF and IF differ in shape/dtype"); return 1;
     }
+    if ((size_t)DFT_TB * d->nf * 16 > 200 * 1024) { set_error("collector: too many frequencies for the blocked DFT (nf <= 800)"); return 1; }
     IES_CUDA(cudaSetDevice(a->cfg.device));
     cudaStream_t st = a->stream;
+    if (st != d->last_stream) {
+        // pending slots were sampled on another stream: accumulate them there first
+        if (dft_flush(d)) return 1;
+        IES_CUDA(cudaStreamSynchronize(d->last_stream));
+        d->last_stream = st;
+    }
     if (b && b->stream != a->stream) {
         IES_CUDA(cudaEventRecord(b->ev_halo, b->stream));
         IES_CUDA(cudaStreamWaitEvent(st, b->ev_halo, 0));
     }
-    k_dft_phase<<<(d->nf + 127) / 128, 128, 0, st>>>(d->freqs, d->nf, (double)tstep, a->cfg.dt, d->phase);
-    DftDev dd; dd.nf = d->nf; dd.ncell = d->ncell;
-    for (int q = 0; q < 4; ++q) dd.acc[q] = d->acc[q];
     const void* fa[4]; const void* fb[4];
     for (int q = 0; q < 4; ++q) { fa[q] = a->F[d->comps[q]]; fb[q] = b ? b->F[d->comps[q]] : nullptr; }
-    DISPATCH(a, k_dft_acc<T, CP><<<(unsigned)((d->ncell + 255) / 256), 256, 0, st>>>(
-        dd, fa[0], fa[1], fa[2], fa[3], fb[0], fb[1], fb[2], fb[3], a->cfg.ny, a->cfg.nz, d->box, d->phase, a->cfg.dt));
-    count_launch(2);
+    d->cplx = a->cplx; d->dt = a->cfg.dt;
+    DISPATCH(a, k_dft_sample<T, CP><<<(unsigned)((d->ncell + 255) / 256), 256, 0, st>>>(
+        d->ring, d->ncell, d->npend, fa[0], fa[1], fa[2], fa[3], fb[0], fb[1], fb[2], fb[3], a->cfg.ny, a->cfg.nz, d->box));
+    count_launch();
     IES_CUDA(cudaGetLastError());
+    d->pend_t[d->npend++] = (double)tstep;
     if (b && b->stream != a->stream) {
         IES_CUDA(cudaEventRecord(a->ev_halo, st));
         IES_CUDA(cudaStreamWaitEvent(b->stream, a->ev_halo, 0));
     }
+    if (d->npend == DFT_TB) return dft_flush(d);
     return 0;
 }
 
 int ies_dft_read(ies_dft* d, int which, void* host) {
     if (which < 0 || which > 3) { set_error("bad index"); return 1; }
     IES_CUDA(cudaSetDevice(d->ctx->cfg.device));
+    if (dft_flush(d)) return 1;
+    IES_CUDA(cudaStreamSynchronize(d->last_stream));
     IES_CUDA(cudaStreamSynchronize(d->ctx->stream));
     IES_CUDA(cudaDeviceSynchronize());
     IES_CUDA(cudaMemcpy(host, d->acc[which], (size_t)d->nf * d->ncell * 16, cudaMemcpyDeviceToHost));
@@ -981,7 +1053,7 @@ int ies_dft_destroy(ies_dft* d) {
     cudaSetDevice(d->ctx->cfg.device);
     cudaDeviceSynchronize();
     for (int q = 0; q < 4; ++q) cudaFree(d->acc[q]);
-    cudaFree(d->freqs); cudaFree(d->phase);
+    cudaFree(d->freqs); cudaFree(d->phase); cudaFree(d->ring);
     delete d;
     return 0;
 }

@@ -141,7 +141,9 @@ int ies_dft_create(ies_ctx* ctx, const int32_t lo[3], const int32_t hi[3],
                    const int32_t comps[4], const double* freqs, int32_t nf, ies_dft** out);
 /* do_RFT(tstep): DFT += (A - B)[box] * exp(2 pi i f tstep dt) * dt.  b may be NULL
  * (plain space) or the incident-field context (Empty3D.get_SF, space.py:2157-2179,
- * evaluated lazily on the collector plane only). */
+ * evaluated lazily on the collector plane only).  The call samples the plane into a ring
+ * of 16 time slots; the accumulators are updated every 16 calls (and on ies_dft_read) in
+ * time order, i.e. with the same arithmetic and summation order as a per-step update. */
 int ies_dft_accumulate(ies_dft* d, ies_ctx* a, ies_ctx* b, int64_t tstep);
 int ies_dft_read(ies_dft* d, int which, void* host_c128);
 int ies_dft_destroy(ies_dft* d);
