@@ -699,7 +699,9 @@ int ies_set_coeff(ies_ctx* c, int half, const double* host, int64_t n) {
     // distinct values; the update kernels then read one index byte per cell instead of 8 bytes
     if (c->cfg.method != IES_FDTD) {
         // per-tile uniform coefficients for the y-line kernel (tile = 4096/ny columns of one plane)
-        const int w = 4096 / c->cfg.ny > 0 ? 4096 / c->cfg.ny : 1;
+        // = YCfg::W of spectral.cuh: 256 threads (128 for complex dtypes, lines up to 1024) / (ny/16)
+        const int thr = (c->cplx && c->cfg.ny / 16 <= 64) ? 128 : 256;
+        const int w = thr * 16 / c->cfg.ny > 0 ? thr * 16 / c->cfg.ny : 1;
         const int kt = (c->cfg.nz + w - 1) / w;
         if (!c->Ctile[half]) { void* p; if (dev_alloc(c, &p, (size_t)c->cfg.nx * kt * 8, false)) return 1; c->Ctile[half] = (double*)p; }
         k_tile_uniform<<<dim3((unsigned)kt, (unsigned)c->cfg.nx), 256, 0, c->stream>>>(

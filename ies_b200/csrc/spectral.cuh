@@ -119,6 +119,18 @@ template <typename T, bool CPLX, int N> struct SCfg {
     static_assert(W * ES >= 32, "row segment below one sector");
 };
 
+// Tile of the fused y-line kernel: W = THREADS/TT adjacent columns x all N rows.  Complex
+// dtypes keep two stash buffers (one per transformed field), so their CTAs are half as wide
+// (128 threads, 64 KB of shared memory for c128) to keep several CTAs per SM.
+template <typename T, bool CPLX, int N> struct YCfg {
+    static constexpr int TT = N / 16;
+    static constexpr int ES = (int)sizeof(T) * (CPLX ? 2 : 1);
+    static constexpr int THREADS = (CPLX && TT <= 64) ? 128 : 256;
+    static constexpr int W = THREADS / TT;
+    static constexpr int MINB = CPLX ? 3 : 2;                     // CTAs per SM the kernel is compiled for
+    static_assert(W >= 1 && W * ES >= 32, "row segment below one sector");
+};
+
 template <typename T, bool CPLX, int N>
 __global__ void __launch_bounds__(SCfg<T, CPLX, N>::THREADS)
 k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict__ dA,
@@ -170,7 +182,7 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
     using C = typename Cx<T>::type;
     using A = typename AccT<CPLX>::type;
     using VV = Vec<T, CPLX>;
-    using S = SCfg<T, CPLX, N>;
+    using S = YCfg<T, CPLX, N>;
     constexpr int W = S::W;
     constexpr int V = VV::V;
     const size_t plane = (size_t)p.ny * p.nz;
@@ -282,14 +294,14 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
 // One CTA = the tile (plane i, columns kb*W .. kb*W+W-1, all rows).  PAL: coefficients come
 // from the palette form (update_dev.cuh ld_coeff).
 template <typename T, bool CPLX, int N, bool PAL, bool SPLIT>
-__global__ void __launch_bounds__(256, (CPLX ? 1 : 2))
+__global__ void __launch_bounds__(YCfg<T, CPLX, N>::THREADS, YCfg<T, CPLX, N>::MINB)
 k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
                const typename Cx<T>::type* __restrict__ ml) {
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
     using A = typename AccT<CPLX>::type;
     using VV = Vec<T, CPLX>;
-    using S = SCfg<T, CPLX, N>;
+    using S = YCfg<T, CPLX, N>;
     constexpr int W = S::W;
     constexpr int V = VV::V;
     constexpr int NF = F::NF;
@@ -429,7 +441,7 @@ int launch_yline_update(Ctx* c, const UpdParams& p, int half, bool split) {
     if (p.i1 <= p.i0) return 0;
     const bool pal = p.Cidx != nullptr;
 #define Y_CASE(NN) {                                                                        \
-        using S = SCfg<T, CPLX, NN>;                                                        \
+        using S = YCfg<T, CPLX, NN>;                                                        \
         size_t sm = sizeof(C) * ((size_t)NN * S::W * Fld<T, CPLX>::NF);                     \
         auto kern = split ? (pal ? k_yline_update<T, CPLX, NN, true, true> : k_yline_update<T, CPLX, NN, false, true>) \
                           : (pal ? k_yline_update<T, CPLX, NN, true, false> : k_yline_update<T, CPLX, NN, false, false>); \
