@@ -39,12 +39,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--only', type=int, default=-1, help='index into CASES')
     args = ap.parse_args()
     import ies_b200
     from ies_b200 import _lib
     lib = _lib.load()
     rows = []
-    for method, dt_, grid in CASES:
+    for method, dt_, grid in (CASES if args.only < 0 else CASES[args.only:args.only + 1]):
         nx, ny, nz = grid
         gap = (720 * um / nx, 512 * um / ny, 512 * um / nz)
         dt = 0.25 * min(gap) / C0

@@ -15,3 +15,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_yl
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_zline -c 1 -f -o gpurun_out/prof_zline \
     python tools/kexp.py --only base --steps 1 --warmup 0 --check-steps 0 > gpurun_out/ncu_full_z.log 2>&1
 ls -la gpurun_out
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fdtd_vec -c 1 -f -o gpurun_out/prof_fdtd \
+    python tools/bench_methods.py --only 0 --steps 1 --warmup 0 > gpurun_out/ncu_full_f.log 2>&1
