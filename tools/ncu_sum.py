@@ -15,7 +15,7 @@ def main(path):
         u = r.get('Metric Unit', '')
         try: v = float(v)
         except ValueError: continue
-        scale = {'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'byte': 1, 'usecond': 1e-6, 'msecond': 1e-3, 'nsecond': 1e-9, 'second': 1}.get(u, 1)
+        scale = {'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'byte': 1, 'usecond': 1e-6, 'msecond': 1e-3, 'nsecond': 1e-9, 'ns': 1e-9, 'us': 1e-6, 'ms': 1e-3, 'second': 1}.get(u, 1)
         agg[k][m] += v * scale
         if (r.get('ID'), k) not in seen:
             seen.add((r.get('ID'), k)); cnt[k] += 1
