@@ -12,6 +12,7 @@
 // real circulant, so D(a + i b) = Da + i Db and no spectrum splitting is needed; the
 // multiplier table is the Hermitian extension of the reference's rfft multiplier.
 #pragma once
+#include <type_traits>
 #include "engine.h"
 #include "fft_dev.cuh"
 #include "update_dev.cuh"
@@ -238,42 +239,58 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
                 ld_coeff<V, CM == 1>(p, idx, cf[u]);
             }
         }
+        // A tile spans all rows, so with CPML on the y faces every tile carries CPML terms; the
+        // rows of this batch may still be interior: then they take the straight-line path too
+        // (batch-uniform branch around two separately compiled bodies).
+        auto compute = [&](auto fastrow, const unsigned bmask) {
+            constexpr bool FR = decltype(fastrow)::value;
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                const int j = tr + (pass0 + u) * RP;
+#pragma unroll
+                for (int v = 0; v < V; ++v) {
+                    A d[6];
+                    const C r0 = xbuf[(size_t)j * W + cg * V + v];
+                    if constexpr (CPLX) {
+                        const C r1 = xbuf[(size_t)N * W + (size_t)j * W + cg * V + v];
+                        d[0] = make_double2((double)r0.x, (double)r0.y);
+                        d[5] = make_double2((double)r1.x, (double)r1.y);
+                    } else {
+                        d[0] = (double)r0.x; d[5] = (double)r0.y;
+                    }
+                    d[1] = dz0[u][v];
+                    if constexpr (SPLIT) {
+                        d[2] = a_zero(A()); d[3] = a_zero(A());
+                        d[4] = nb_any ? a_scale(sx, a_sub(a4[u][v], b4[u][v])) : a_zero(A());
+                        A gg[3] = {g[u][0][v], a_zero(A()), g[u][2][v]};
+                        if constexpr (FR) cell_update_fast<CPLX, 5>(upd, cf[u][v], d, gg);
+                        else cell_update_regs<T, CPLX, 5>(p, bmask, i, j, k + v, cf[u][v], d, gg);
+                        g[u][0][v] = gg[0]; g[u][2][v] = gg[2];
+                    } else {
+                        d[2] = dz1[u][v];
+                        if (p.pstd) { d[3] = a3[u][v]; d[4] = a4[u][v]; }
+                        else if (nb_any) {
+                            d[3] = a_scale(sx, a_sub(a3[u][v], b3[u][v]));
+                            d[4] = a_scale(sx, a_sub(a4[u][v], b4[u][v]));
+                        } else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
+                        A gg[3] = {g[u][0][v], g[u][1][v], g[u][2][v]};
+                        if constexpr (FR) cell_update_fast<CPLX>(upd, cf[u][v], d, gg);
+                        else cell_update_regs<T, CPLX>(p, bmask, i, j, k + v, cf[u][v], d, gg);
+                        g[u][0][v] = gg[0]; g[u][1][v] = gg[1]; g[u][2][v] = gg[2];
+                    }
+                }
+            }
+        };
+        if constexpr (FAST) {
+            compute(std::true_type{}, 0u);
+        } else {
+            const unsigned bm = term_mask(p, i, i + 1, pass0 * RP, (pass0 + PB) * RP, k0, k0 + W);
+            if (upd >= 0 && bm == 0u) compute(std::true_type{}, 0u); else compute(std::false_type{}, bm);
+        }
 #pragma unroll
         for (int u = 0; u < PB; ++u) {
             const int j = tr + (pass0 + u) * RP;
             const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                A d[6];
-                const C r0 = xbuf[(size_t)j * W + cg * V + v];
-                if constexpr (CPLX) {
-                    const C r1 = xbuf[(size_t)N * W + (size_t)j * W + cg * V + v];
-                    d[0] = make_double2((double)r0.x, (double)r0.y);
-                    d[5] = make_double2((double)r1.x, (double)r1.y);
-                } else {
-                    d[0] = (double)r0.x; d[5] = (double)r0.y;
-                }
-                d[1] = dz0[u][v];
-                if constexpr (SPLIT) {
-                    d[2] = a_zero(A()); d[3] = a_zero(A());
-                    d[4] = nb_any ? a_scale(sx, a_sub(a4[u][v], b4[u][v])) : a_zero(A());
-                    A gg[3] = {g[u][0][v], a_zero(A()), g[u][2][v]};
-                    if constexpr (FAST) cell_update_fast<CPLX, 5>(upd, cf[u][v], d, gg);
-                    else cell_update_regs<T, CPLX, 5>(p, mask, i, j, k + v, cf[u][v], d, gg);
-                    g[u][0][v] = gg[0]; g[u][2][v] = gg[2];
-                } else {
-                    d[2] = dz1[u][v];
-                    if (p.pstd) { d[3] = a3[u][v]; d[4] = a4[u][v]; }
-                    else if (nb_any) {
-                        d[3] = a_scale(sx, a_sub(a3[u][v], b3[u][v]));
-                        d[4] = a_scale(sx, a_sub(a4[u][v], b4[u][v]));
-                    } else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
-                    A gg[3] = {g[u][0][v], g[u][1][v], g[u][2][v]};
-                    if constexpr (FAST) cell_update_fast<CPLX>(upd, cf[u][v], d, gg);
-                    else cell_update_regs<T, CPLX>(p, mask, i, j, k + v, cf[u][v], d, gg);
-                    g[u][0][v] = gg[0]; g[u][1][v] = gg[1]; g[u][2][v] = gg[2];
-                }
-            }
             if constexpr (SPLIT) {
                 VV::st(p.G[0], idx, g[u][0]);
                 VV::st(p.G[2], idx, g[u][2]);

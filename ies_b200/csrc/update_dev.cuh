@@ -139,30 +139,35 @@ __device__ __forceinline__ void cell_update_regs(const UpdParams& p, unsigned ma
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
         if (!(COMPS & (1 << c))) continue;
-        const A da = d[2 * c], db = d[2 * c + 1];
         if (in_box(p.box[c].lo, p.box[c].hi, i, j, k))
-            g[c] = a_add(g[c], a_scale(C, a_sub(da, db)));
-        unsigned m = mask;
-        while (m) {
-            const int t = __ffs(m) - 1;
-            m &= m - 1;
-            const PmlTermDev& q = p.terms[t];
-            if (q.comp != c || !in_box(q.lo, q.hi, i, j, k)) continue;
-            const int ax = q.axis;
-            const int n = (ax == 0 ? i - q.lo[0] : ax == 1 ? j - q.lo[1] : k - q.lo[2]);
-            const int pn = n + q.psi_off;
-            const int p0 = ax == 0 ? pn : i, p1 = ax == 1 ? pn : j, p2 = ax == 2 ? pn : k;
-            const size_t pidx = ((size_t)p0 * q.pdim[1] + p1) * q.pdim[2] + p2;
-            const A dd = (q.diff & 1) ? db : da;
-            A psi = E::ld(q.psi, pidx);
-            psi = a_add(a_scale(q.b[n], psi), a_scale(q.a[n], dd));
-            // psi is stored in field precision and the rounded value is what the
-            // field correction uses (space.py:1154-1156)
-            E::st(q.psi, pidx, psi);
-            psi = E::rnd(psi);
-            const A corr = a_scale(C, a_add(a_scale(q.kf[n], dd), psi));
-            g[c] = a_add(g[c], a_scale(q.sign, corr));
-        }
+            g[c] = a_add(g[c], a_scale(C, a_sub(d[2 * c], d[2 * c + 1])));
+    }
+    // CPML terms, one walk over the set bits (terms are stored in the order the reference
+    // applies them, so each component still receives its corrections in that order)
+    unsigned m = mask;
+    while (m) {
+        const int t = __ffs(m) - 1;
+        m &= m - 1;
+        const PmlTermDev& q = p.terms[t];
+        const int c = q.comp;
+        if (!((COMPS >> c) & 1) || !in_box(q.lo, q.hi, i, j, k)) continue;
+        const int ax = q.axis;
+        const int n = (ax == 0 ? i - q.lo[0] : ax == 1 ? j - q.lo[1] : k - q.lo[2]);
+        const int pn = n + q.psi_off;
+        const int p0 = ax == 0 ? pn : i, p1 = ax == 1 ? pn : j, p2 = ax == 2 ? pn : k;
+        const size_t pidx = ((size_t)p0 * q.pdim[1] + p1) * q.pdim[2] + p2;
+        const int df = q.diff;                          // derivative slot 0..5 (register select, no local array)
+        const A dd = df == 0 ? d[0] : df == 1 ? d[1] : df == 2 ? d[2] : df == 3 ? d[3] : df == 4 ? d[4] : d[5];
+        A psi = E::ld(q.psi, pidx);
+        psi = a_add(a_scale(q.b[n], psi), a_scale(q.a[n], dd));
+        // psi is stored in field precision and the rounded value is what the
+        // field correction uses (space.py:1154-1156)
+        E::st(q.psi, pidx, psi);
+        psi = E::rnd(psi);
+        const A corr = a_scale(q.sign, a_scale(C, a_add(a_scale(q.kf[n], dd), psi)));
+        if (c == 0) g[0] = a_add(g[0], corr);
+        else if (c == 1) g[1] = a_add(g[1], corr);
+        else g[2] = a_add(g[2], corr);
     }
 }
 

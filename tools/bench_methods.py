@@ -29,6 +29,9 @@ CASES = [
     ('SHPF', np.complex128, (512, 256, 256)),
     ('SHPF', np.float64, (512, 512, 512)),
     ('SHPF', np.float64, (2048, 128, 128)),
+    ('SHPF-allpml', np.float64, (1024, 256, 256)),
+    ('SHPF-allpml', np.float64, (256, 512, 512)),
+    ('FDTD-allpml', np.float64, (1024, 256, 256)),
     ('PSTD', np.complex128, (128, 128, 128)),
     ('PSTD', np.float64, (512, 256, 256)),
 ]
@@ -46,6 +49,9 @@ def main():
     lib = _lib.load()
     rows = []
     for method, dt_, grid in (CASES if args.only < 0 else CASES[args.only:args.only + 1]):
+        allpml = method.endswith('-allpml')
+        label = method
+        method = method.split('-')[0]
         nx, ny, nz = grid
         gap = (720 * um / nx, 512 * um / ny, 512 * um / nz)
         dt = 0.25 * min(gap) / C0
@@ -53,9 +59,11 @@ def main():
         sp = ies_b200.space.Basic3D(grid, gap, dt, 1000, dt_, np.complex128 if np.dtype(dt_).itemsize in (8, 16) else np.complex64,
                                     method=method, engine='b200')
         sp.malloc()
-        pml = {'x': '+-' if method != 'PSTD' or True else '', 'y': '', 'z': ''}
+        pml = {'x': '+-', 'y': '+-' if allpml else '', 'z': '+-' if allpml else ''}
         sp.apply_PML(pml, 10)
-        if cplx:
+        if allpml:
+            pass
+        elif cplx:
             sp.apply_BBC({'x': False, 'y': True, 'z': True}); sp.apply_PBC({'x': False, 'y': False, 'z': False})
         else:
             sp.apply_BBC({'x': False, 'y': False, 'z': False}); sp.apply_PBC({'x': False, 'y': True, 'z': True})
@@ -80,7 +88,7 @@ def main():
         ncell = nx * ny * nz
         g = ncell / per / 1e6
         finite = bool(np.all(np.isfinite(np.asarray(sp.Ey[nx // 2, :4, :4]))))
-        row = dict(method=method, dtype=np.dtype(dt_).name, grid=list(grid), ms_per_step=round(per, 4), gcell_s=round(g, 2),
+        row = dict(method=label, dtype=np.dtype(dt_).name, grid=list(grid), ms_per_step=round(per, 4), gcell_s=round(g, 2),
                    gbs_algorithmic=round(g * BYTES[dt_], 0), finite=finite)
         rows.append(row)
         print(json.dumps(row), flush=True)
