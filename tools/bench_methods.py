@@ -43,12 +43,14 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--only', type=int, default=-1, help='index into CASES')
+    ap.add_argument('--grep', default='', help='only cases whose label/grid string contains this')
     args = ap.parse_args()
     import ies_b200
     from ies_b200 import _lib
     lib = _lib.load()
     rows = []
     for method, dt_, grid in (CASES if args.only < 0 else CASES[args.only:args.only + 1]):
+        if args.grep and args.grep not in f'{method} {np.dtype(dt_).name} {grid}': continue
         allpml = method.endswith('-allpml')
         label = method
         method = method.split('-')[0]
