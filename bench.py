@@ -172,7 +172,7 @@ def run_reference_arm(args, rank, world):
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
-    R = max(1, min(cores, 64))
+    R = max(1, min(cores, 64, int(os.environ.get('IES_BENCH_REF_MAX_RANKS', 64))))
     nx_s = 16
     # keep the whole run within a few minutes: ~0.35 s per rank-step at 16x256x256
     steps = max(1, min(args.steps, 60))
