@@ -92,3 +92,70 @@ def test_collectors_and_probe_vs_reference_api_oracle(product, tmp_path):
         assert rel(getattr(r['probe'], n + '_t'), sig[n]) <= 1e-10, n
     # lazy scattered field read back on the host equals TF - IF
     assert rel(np.asarray(r['SF'].Ey), TF.Ey - IF.Ey) <= 1e-10
+
+
+@pytest.mark.parametrize('ranks', [1, 2])
+def test_sy_sz_collectors_vs_stepwise_numpy_dft(product, tmp_path, ranks):
+    """Sy / Sz (collector.py:387-801) on the device (time-blocked accumulation, planes spanning the
+    x-slabs) against the reference's formula applied step by step in NumPy to the fields read back
+    after every step (collector.py:508-527, 716-735)."""
+    from oracle import cases as C
+    from ies_b200 import comm
+    case = dict(C.CASES_BY_NAME['shpf_f64_allpml'])
+    steps = 37                                   # two full blocks of 16 + a partial one
+    (Lx, Ly, Lz), gap, dt = C.geometry(case)
+    grp = comm.LocalGroup(ranks)
+    spaces, setters, sys_, szs = [], [], [], []
+    wv = np.linspace(60e-6, 90e-6, 7)
+    freqs = 299792458.0 / wv
+    path = str(tmp_path) + '/'
+    for r in range(ranks):
+        kw = dict(method='SHPF', engine='b200')
+        if ranks > 1: kw['comm'] = grp.comm(r)
+        sp = product.space.Basic3D(case['grid'], gap, dt, steps + 1, np.float64, np.complex128, **kw)
+        sp.malloc()
+        sp.apply_PML(case['pml'], case['npml'])
+        s0, s1 = C.source_box(case)
+        setters.append(product.source.Setter(sp, s0, s1, case['mmt']))
+        for (b0, b1, er, mr) in C.box_list(case):
+            product.structure.Box('box', sp, b0, b1, er, mr)
+        sp.init_update_constants()
+        spaces.append(sp)
+        sys_.append(product.collector.Sy('sy', path, sp, 0.4 * Ly, (0.1 * Lx, 0.2 * Lz), (0.9 * Lx, 0.8 * Lz), freqs, 'b200'))
+        szs.append(product.collector.Sz('sz', path, sp, 0.6 * Lz, (0.1 * Lx, 0.2 * Lz), (0.9 * Lx, 0.8 * Lz), freqs, 'b200'))
+    c0 = sys_[0]
+    X0, X1, Z0, Z1, Yc = c0.xsrt, c0.xend, c0.zsrt, c0.zend, c0.ysrt
+    d0 = szs[0]
+    YS, YE, Zc = d0.ysrt, d0.yend, d0.zsrt
+    want = {n: 0 for n in ('yEx', 'yEz', 'yHx', 'yHz', 'zEx', 'zEy', 'zHx', 'zHy')}
+    full = lambda n: np.concatenate([np.asarray(getattr(sp, n)[:, :, :]) for sp in spaces], axis=0)
+    f = freqs[:, None, None]
+    for t in range(steps):
+        pv = C.pulse_value(case, t, dt)
+        for s in setters: s.put_src(case['src_field'], pv, case['put'])
+        for sp in spaces: sp.updateH(t)
+        for sp in spaces: sp.updateE(t)
+        for c in sys_ + szs: c.do_RFT(t)
+        ph = np.exp(2.j * np.pi * f * t * dt) * dt
+        F = {n: full(n) for n in ('Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz')}
+        want['yEx'] = want['yEx'] + F['Ex'][X0:X1, Yc, Z0:Z1] * ph
+        want['yEz'] = want['yEz'] + F['Ez'][X0:X1, Yc, Z0:Z1] * ph
+        want['yHx'] = want['yHx'] + F['Hx'][X0:X1, Yc, Z0:Z1] * ph
+        want['yHz'] = want['yHz'] + F['Hz'][X0:X1, Yc, Z0:Z1] * ph
+        want['zEx'] = want['zEx'] + F['Ex'][X0:X1, YS:YE, Zc] * ph
+        want['zEy'] = want['zEy'] + F['Ey'][X0:X1, YS:YE, Zc] * ph
+        want['zHx'] = want['zHx'] + F['Hx'][X0:X1, YS:YE, Zc] * ph
+        want['zHy'] = want['zHy'] + F['Hy'][X0:X1, YS:YE, Zc] * ph
+    # one process plays all ranks: the other ranks save their parts before rank 0 concatenates
+    for c in reversed(sys_): c.get_Sy(steps)
+    for c in reversed(szs): c.get_Sz(steps)
+    got_sy, got_sz = sys_[0], szs[0]                      # rank 0 holds the concatenated result
+    Sy = 0.5 * (-(want['yEx'].real * want['yHz'].real) - (want['yEx'].imag * want['yHz'].imag)
+                + (want['yEz'].real * want['yHx'].real) + (want['yEz'].imag * want['yHx'].imag))
+    Sz = 0.5 * (-(want['zEy'].real * want['zHx'].real) - (want['zEy'].imag * want['zHx'].imag)
+                + (want['zEx'].real * want['zHy'].real) + (want['zEx'].imag * want['zHy'].imag))
+    assert got_sy.Sy.shape == Sy.shape and got_sz.Sz.shape == Sz.shape
+    assert np.linalg.norm(Sy) > 0 and np.linalg.norm(Sz) > 0
+    assert rel(got_sy.Sy, Sy) <= 1e-10, rel(got_sy.Sy, Sy)
+    assert rel(got_sz.Sz, Sz) <= 1e-10, rel(got_sz.Sz, Sz)
+    assert rel(got_sy.Sy_area, Sy.sum(axis=(1, 2)) * spaces[0].dx * spaces[0].dz) <= 1e-10
