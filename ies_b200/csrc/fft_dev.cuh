@@ -120,9 +120,9 @@ __device__ __forceinline__ void fft_stage_v(C (&v)[VPT], const int t, const C* _
             constexpr int step = N / (NS * R);
 #pragma unroll
             for (int m = 1; m < R; ++m) {
-                // TWT: tw is the stage table transposed to [m][jj] (consecutive threads read
-                // consecutive entries: no shared-memory bank conflicts); only valid when all
-                // twiddled stages of the plan share one (R, NS) pair, e.g. N = VPT * VPT
+                // TWT: tw is THIS stage's table transposed to [m][jj], row length NS (consecutive
+                // threads read consecutive entries: no shared-memory bank conflicts); else the
+                // master table W_N[k]
                 const C w = TWT ? tw[m * NS + jj] : tw[(jj * m * step) & (N - 1)];
                 in[m] = INV ? cmulc(in[m], w) : cmul(in[m], w);
             }
@@ -149,35 +149,48 @@ template <int N, int VPT> __device__ __forceinline__ int spec_index_v(int t, int
 // Line index held in v[q] before fft_forward and after fft_inverse.
 template <int N, int VPT> __device__ __forceinline__ int line_index_v(int t, int q) { return t + q * (N / VPT); }
 
+// Transposed stage tables (TWT): twf = table of the second forward stage (radix R1, NS = VPT):
+// twf[m*VPT + jj] = W_N^(jj*m*N/(VPT*R1)); twi = table of the last inverse stage (radix VPT,
+// NS = N/VPT): twi[m*(N/VPT) + jj] = W_N^(jj*m).  For N = VPT*VPT both are the same table.
+// The remaining twiddled stages (only when R2 > 1) read the master table tw.
+template <int N, int VPT> struct TwTables {
+    using P = PlanV<N, VPT>;
+    static constexpr int FWD = (N > VPT) ? P::R1 * VPT : 0;          // entries of twf
+    static constexpr int INV = (N > VPT) ? N : 0;                    // entries of twi
+    static constexpr bool SHARED = (N == VPT * VPT);                 // twf == twi
+    static constexpr bool NEED_MASTER = P::R2 > 1;
+    static constexpr int FSTEP = (N > VPT) ? N / (VPT * P::R1) : 1;
+};
+
 template <int N, int VPT, bool TWT = false, typename C, typename X>
-__device__ __forceinline__ void fft_forward_v(C (&v)[VPT], int t, const C* tw, X& xb) {
+__device__ __forceinline__ void fft_forward_v(C (&v)[VPT], int t, const C* tw, X& xb, const C* twf = nullptr) {
     using P = PlanV<N, VPT>;
     if (N == VPT) {
-        fft_stage_v<N, VPT, VPT, 1, false, false, false, TWT>(v, t, tw, xb);
+        fft_stage_v<N, VPT, VPT, 1, false, false, false>(v, t, tw, xb);
     } else {
-        fft_stage_v<N, VPT, VPT, 1, false, false, true, TWT>(v, t, tw, xb);
+        fft_stage_v<N, VPT, VPT, 1, false, false, true>(v, t, tw, xb);
         if (P::R2 == 1) {
-            fft_stage_v<N, VPT, P::R1, VPT, false, true, false, TWT>(v, t, tw, xb);
+            fft_stage_v<N, VPT, P::R1, VPT, false, true, false, TWT>(v, t, TWT ? twf : tw, xb);
         } else {
-            fft_stage_v<N, VPT, P::R1, VPT, false, true, true, TWT>(v, t, tw, xb);
+            fft_stage_v<N, VPT, P::R1, VPT, false, true, true, TWT>(v, t, TWT ? twf : tw, xb);
             fft_stage_v<N, VPT, (P::R2 > 1 ? P::R2 : 2), VPT * P::R1, false, true, false>(v, t, tw, xb);
         }
     }
 }
 
 template <int N, int VPT, bool TWT = false, typename C, typename X>
-__device__ __forceinline__ void fft_inverse_v(C (&v)[VPT], int t, const C* tw, X& xb) {
+__device__ __forceinline__ void fft_inverse_v(C (&v)[VPT], int t, const C* tw, X& xb, const C* twi = nullptr) {
     using P = PlanV<N, VPT>;
     if (N == VPT) {
-        fft_stage_v<N, VPT, VPT, 1, true, false, false, TWT>(v, t, tw, xb);
+        fft_stage_v<N, VPT, VPT, 1, true, false, false>(v, t, tw, xb);
     } else if (P::R2 == 1) {
-        fft_stage_v<N, VPT, P::R1, 1, true, false, true, TWT>(v, t, tw, xb);
-        fft_stage_v<N, VPT, VPT, P::R1, true, true, false, TWT>(v, t, tw, xb);
+        fft_stage_v<N, VPT, P::R1, 1, true, false, true>(v, t, tw, xb);
+        fft_stage_v<N, VPT, VPT, P::R1, true, true, false, TWT>(v, t, TWT ? twi : tw, xb);
     } else {
         constexpr int R2 = (P::R2 > 1 ? P::R2 : 2);
-        fft_stage_v<N, VPT, R2, 1, true, false, true, TWT>(v, t, tw, xb);
-        fft_stage_v<N, VPT, P::R1, R2, true, true, true, TWT>(v, t, tw, xb);
-        fft_stage_v<N, VPT, VPT, R2 * P::R1, true, true, false, TWT>(v, t, tw, xb);
+        fft_stage_v<N, VPT, R2, 1, true, false, true>(v, t, tw, xb);
+        fft_stage_v<N, VPT, P::R1, R2, true, true, true>(v, t, tw, xb);
+        fft_stage_v<N, VPT, VPT, R2 * P::R1, true, true, false, TWT>(v, t, TWT ? twi : tw, xb);
     }
 }
 

@@ -68,23 +68,29 @@ k_zline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
     using X = typename ZXchg<C, N, VPT>::type;
+    // Shared-memory tables: the twiddles of the second forward and the last inverse stage
+    // transposed to [m][jj] (the threads of a line read consecutive entries; the master
+    // table's stride-m access costs 2.1x the wavefronts at N = 256 and more at N = 512), the
+    // master table only when a third stage needs it, and the spectral multiplier.
+    using TT_ = TwTables<N, VPT>;
+    using P = PlanV<N, VPT>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    C* tw = reinterpret_cast<C*>(smem_raw);
-    C* ml = tw + N;
+    C* tw = reinterpret_cast<C*>(smem_raw);                       // master (TT_::NEED_MASTER ? N : 0)
+    C* twf = tw + (TT_::NEED_MASTER ? N : 0);
+    C* twi = TT_::SHARED ? twf : twf + TT_::FWD;
+    C* ml = twi + TT_::INV;
     C* xbuf = ml + N;
-    // N = VPT*VPT: both twiddled stages use W_N^(jj*m), jj, m < VPT; the table is laid out
-    // [m][jj] so that the threads of a line read consecutive entries (the master table's
-    // stride-m access costs 2.1x the wavefronts).
-    constexpr bool TWT = (N == VPT * VPT);
-    if constexpr (TWT) {
-        for (int q = threadIdx.x; q < N; q += blockDim.x) {
-            tw[q] = twg[((q / VPT) * (q % VPT)) & (N - 1)];
-            ml[q] = mlg[q];
+    for (int q = threadIdx.x; q < N; q += blockDim.x) {
+        ml[q] = mlg[q];
+        if (TT_::NEED_MASTER) tw[q] = twg[q];
+        if (N > VPT) {
+            constexpr int NSI = N / VPT;
+            twi[q] = twg[((q / NSI) * (q % NSI)) & (N - 1)];
+            if (!TT_::SHARED && q < TT_::FWD) twf[q] = twg[((q / VPT) * (q % VPT) * TT_::FSTEP) & (N - 1)];
         }
-        __syncthreads();
-    } else {
-        load_tables(tw, ml, twg, mlg, N);
     }
+    __syncthreads();
+    constexpr bool TWT = N > VPT;
     constexpr int TT = ZCfg<N, VPT>::TT, LPB = ZCfg<N, VPT>::LPB;
     const int t = threadIdx.x % TT, l = threadIdx.x / TT;
     const long line = (long)blockIdx.x * LPB + l;
@@ -100,10 +106,10 @@ k_zline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
             if (ok) v[q] = F::ld(A, B, ibase + line_index_v<N, VPT>(t, q), f);
             else { v[q].x = 0; v[q].y = 0; }
         }
-        fft_forward_v<N, VPT, TWT>(v, t, tw, xb);
+        fft_forward_v<N, VPT, TWT>(v, t, tw, xb, twf);
 #pragma unroll
         for (int q = 0; q < VPT; ++q) v[q] = cmul(v[q], ml[spec_index_v<N, VPT>(t, q)]);
-        fft_inverse_v<N, VPT, TWT>(v, t, tw, xb);
+        fft_inverse_v<N, VPT, TWT>(v, t, tw, xb, twi);
         if (ok) {
 #pragma unroll
             for (int q = 0; q < VPT; ++q) F::st(dA, dB, obase + line_index_v<N, VPT>(t, q), v[q], f);
@@ -398,7 +404,9 @@ int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
     if (nlines <= 0) return 0;
 #define Z_LAUNCH(NN, VV) {                                                                  \
         constexpr int LPB = ZCfg<NN, VV>::LPB;                                              \
-        size_t sm = sizeof(C) * (2 * NN + (size_t)LPB * ZXchg<C, NN, VV>::type::LS);        \
+        using TW = TwTables<NN, VV>;                                                        \
+        size_t sm = sizeof(C) * ((TW::NEED_MASTER ? NN : 0) + (TW::SHARED ? 0 : TW::FWD) + TW::INV + NN + \
+                                 (size_t)LPB * ZXchg<C, NN, VV>::type::LS);                  \
         auto kern = k_zline<T, CPLX, NN, VV>;                                               \
         if (set_smem(kern, sm)) return 1;                                                   \
         unsigned grid = (unsigned)((nlines + LPB - 1) / LPB);                               \

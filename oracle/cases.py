@@ -62,8 +62,7 @@ CASES = [
     _case('pstd_c64_xpml', 'PSTD', 'complex64', (32, 16, 16), src='plane'),
     _case('pstd_f64_nopml_hard', 'PSTD', 'float64', (16, 16, 32), pml=NOPML, src='point', put='hard'),
 ]
-# Larger live-only cases (no golden file; compared with the oracle at test time).  ny = nz >= 64
-# exercises the fused persistent SHPF kernel including its scratch-ring wrap-around.
+# Larger live-only cases (no golden file; compared with the oracle at test time).
 LIVE_CASES = [
     _case('shpf_f64_xpml_64', 'SHPF', 'float64', (40, 64, 64), steps=10, npml=6, pbc=PBC_YZ, bbc=NO),
     _case('shpf_f64_allpml_64_r2', 'SHPF', 'float64', (40, 64, 64), steps=10, npml=6, pml=ALLPML, src='point', ranks=2),
@@ -72,8 +71,11 @@ LIVE_CASES = [
     _case('shpf_c128_bloch_yz_128', 'SHPF', 'complex128', (28, 128, 128), steps=6, bbc=BBC_YZ, pbc=NO, mmt=K1, src='point'),
     _case('shpf_f64_xpml_16x64', 'SHPF', 'float64', (24, 16, 64), steps=10, pbc=PBC_YZ, bbc=NO),
     _case('pstd_f64_xpml_64', 'PSTD', 'float64', (64, 32, 64), steps=8, npml=6, src='plane'),
-    # sources on the components whose derivative the alternating SHPF path precomputes one
-    # half-step early (E_z, E_x before updateH; H_y, H_x before updateE): scratch refresh
+    # long lines: three-stage FFT plans (radix 16/16/2 at 512), every power of two in between
+    _case('shpf_f64_z512_y128', 'SHPF', 'float64', (12, 128, 512), steps=6, npml=4, pbc=PBC_YZ, bbc=NO, src='point'),
+    _case('shpf_f64_y512_z32', 'SHPF', 'float64', (12, 512, 32), steps=6, npml=4, pml=ALLPML, src='point'),
+    _case('shpf_c64_z512_y16', 'SHPF', 'complex64', (12, 16, 512), steps=6, npml=4, pbc=PBC_YZ, bbc=NO, src='point'),
+    # sources on every kind of component (E_z, E_x, H_y, H_x; soft / hard; point / plane)
     _case('shpf_f64_src_ez', 'SHPF', 'float64', (24, 32, 32), steps=10, pbc=PBC_YZ, bbc=NO, src='point', src_field='Ez'),
     _case('shpf_f64_src_ex_hard', 'SHPF', 'float64', (24, 32, 32), steps=10, pml=ALLPML, src='point', src_field='Ex', put='hard'),
     _case('shpf_f64_src_hy_r2', 'SHPF', 'float64', (24, 32, 32), steps=10, pbc=PBC_YZ, bbc=NO, src='point', src_field='Hy', ranks=2),
