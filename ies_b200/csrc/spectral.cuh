@@ -202,7 +202,10 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
     constexpr int CG = W / V;                    // column groups
     constexpr int RP = S::THREADS / CG;          // rows per pass
     constexpr int NPASS = N / RP;
-    constexpr int PB = (NPASS % 2 == 0) ? 2 : 1; // passes whose loads are batched
+    // passes whose loads are batched: two when one pass takes 40 registers (f64: 2 cells per
+    // vector, c128: 1), one when it takes 80 (f32: 4 cells, c64: 2 complex cells) -- two such
+    // passes spilled (f32 SHPF 24.6 -> 32.8 Gcell/s with one)
+    constexpr int PB = (NPASS % 2 == 0 && V * (CPLX ? 2 : 1) <= 2) ? 2 : 1;
     const int cg = threadIdx.x % CG, tr = threadIdx.x / CG;
     const int k = k0 + cg * V;
     if (k >= p.nz) return;
