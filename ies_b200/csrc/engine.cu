@@ -134,7 +134,7 @@ __device__ __forceinline__ void fdtd_vec_body(const UpdParams& p, const unsigned
         g[0][v] = gg[0]; g[1][v] = gg[1]; g[2][v] = gg[2];
     }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) VV::st(p.G[c], idx, g[c]);
+    for (int c = 0; c < 3; ++c) vst_stream<VV>(p.G[c], idx, g[c], 0);     // st.global.cs (not re-read in this half-step)
 }
 
 template <typename T, bool CPLX, bool PAL>

@@ -66,6 +66,13 @@ template <> struct Vec<double, false> {
     static __device__ __forceinline__ void ld(const void* p, size_t i, double (&o)[2]) {
         const double2 v = *reinterpret_cast<const double2*>((const double*)p + i); o[0] = v.x; o[1] = v.y;
     }
+    // streaming variants (ld/st.global.cs: evict-first): for data touched once per half-step
+    static __device__ __forceinline__ void ld_stream(const void* p, size_t i, double (&o)[2]) {
+        const double2 v = __ldcs(reinterpret_cast<const double2*>((const double*)p + i)); o[0] = v.x; o[1] = v.y;
+    }
+    static __device__ __forceinline__ void st_stream(void* p, size_t i, const double (&o)[2]) {
+        __stcs(reinterpret_cast<double2*>((double*)p + i), make_double2(o[0], o[1]));
+    }
     static __device__ __forceinline__ void st(void* p, size_t i, const double (&o)[2]) {
         *reinterpret_cast<double2*>((double*)p + i) = make_double2(o[0], o[1]);
     }
@@ -79,6 +86,9 @@ template <> struct Vec<float, false> {
     static __device__ __forceinline__ void st(void* p, size_t i, const double (&o)[4]) {
         *reinterpret_cast<float4*>((float*)p + i) = make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]);
     }
+    static __device__ __forceinline__ void st_stream(void* p, size_t i, const double (&o)[4]) {
+        __stcs(reinterpret_cast<float4*>((float*)p + i), make_float4((float)o[0], (float)o[1], (float)o[2], (float)o[3]));
+    }
 };
 template <> struct Vec<float, true> {
     static constexpr int V = 2;
@@ -90,12 +100,26 @@ template <> struct Vec<float, true> {
         *reinterpret_cast<float4*>((float2*)p + i) =
             make_float4((float)o[0].x, (float)o[0].y, (float)o[1].x, (float)o[1].y);
     }
+    static __device__ __forceinline__ void st_stream(void* p, size_t i, const double2 (&o)[2]) {
+        __stcs(reinterpret_cast<float4*>((float2*)p + i),
+               make_float4((float)o[0].x, (float)o[0].y, (float)o[1].x, (float)o[1].y));
+    }
 };
 template <> struct Vec<double, true> {
     static constexpr int V = 1;
     static __device__ __forceinline__ void ld(const void* p, size_t i, double2 (&o)[1]) { o[0] = ((const double2*)p)[i]; }
     static __device__ __forceinline__ void st(void* p, size_t i, const double2 (&o)[1]) { ((double2*)p)[i] = o[0]; }
+    static __device__ __forceinline__ void st_stream(void* p, size_t i, const double2 (&o)[1]) { __stcs((double2*)p + i, o[0]); }
 };
+// Streaming accessors: Vec<T,CPLX>::ld_stream / st_stream when the specialisation has them
+// (fp64 real), else the plain ones.
+template <typename VV, typename X, int V> __device__ __forceinline__ auto vld_stream(const void* p, size_t i, X (&o)[V], int)
+    -> decltype(VV::ld_stream(p, i, o)) { VV::ld_stream(p, i, o); }
+template <typename VV, typename X, int V> __device__ __forceinline__ void vld_stream(const void* p, size_t i, X (&o)[V], long) { VV::ld(p, i, o); }
+template <typename VV, typename X, int V> __device__ __forceinline__ auto vst_stream(void* p, size_t i, const X (&o)[V], int)
+    -> decltype(VV::st_stream(p, i, o)) { VV::st_stream(p, i, o); }
+template <typename VV, typename X, int V> __device__ __forceinline__ void vst_stream(void* p, size_t i, const X (&o)[V], long) { VV::st(p, i, o); }
+
 // Coefficients of V consecutive cells: from the palette form (one index byte per cell, the
 // palette in the kernel-parameter constant bank) when PAL, else from the f64 array.
 template <int V, bool PAL> __device__ __forceinline__ void ld_coeff(const UpdParams& q, size_t i, double (&o)[V]) {
