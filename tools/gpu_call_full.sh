@@ -10,10 +10,10 @@ timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/b
 cut -c1-300 gpurun_out/bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 3 --warmup 3 > gpurun_out/bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_yline_update -c 1 -f -o gpurun_out/prof_yline \
-    python tools/kexp.py --only base --steps 1 --warmup 0 --check-steps 0 > gpurun_out/ncu_full_y.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_zline -c 1 -f -o gpurun_out/prof_zline \
-    python tools/kexp.py --only base --steps 1 --warmup 0 --check-steps 0 > gpurun_out/ncu_full_z.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_yline_update --launch-skip 2 -c 1 -f -o gpurun_out/prof_yline \
+    python tools/kexp.py --only base --steps 2 --warmup 0 --check-steps 0 > gpurun_out/ncu_full_y.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_zline --launch-skip 2 -c 1 -f -o gpurun_out/prof_zline \
+    python tools/kexp.py --only base --steps 2 --warmup 0 --check-steps 0 > gpurun_out/ncu_full_z.log 2>&1
 ls -la gpurun_out
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_fdtd_vec -c 1 -f -o gpurun_out/prof_fdtd \
     python tools/bench_methods.py --only 0 --steps 1 --warmup 0 > gpurun_out/ncu_full_f.log 2>&1
