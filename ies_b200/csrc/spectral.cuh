@@ -177,7 +177,7 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
         fft_inverse<N>(v, t, tw, xb);
         if (ok) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) F::st(dA, dB, boff + (size_t)line_index<N>(t, q) * stride + col, v[q], f);
+            for (int q = 0; q < 16; ++q) F::st_stream(dA, dB, boff + (size_t)line_index<N>(t, q) * stride + col, v[q], f);
         }
     }
 }
