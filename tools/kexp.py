@@ -22,9 +22,10 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 VARIANTS = [
-    ('base', dict(split=0, ctile=0)),
-    ('ctile', dict(split=0, ctile=1)),
-    ('split_ctile', dict(split=1, ctile=1)),
+    ('base', dict()),                                   # engine defaults
+    ('noctile', dict(ctile=0)),
+    ('split', dict(split=1)),
+    ('palette', dict(palette=1, ctile=0)),
 ]
 ALL_OPTS = ('split', 'palette', 'ctile')
 DEFAULTS = dict(split=0, palette=0, ctile=1)
