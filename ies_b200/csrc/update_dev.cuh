@@ -116,12 +116,8 @@ template <> struct Vec<double, true> {
 template <typename VV, typename X, int V> __device__ __forceinline__ auto vld_stream(const void* p, size_t i, X (&o)[V], int)
     -> decltype(VV::ld_stream(p, i, o)) { VV::ld_stream(p, i, o); }
 template <typename VV, typename X, int V> __device__ __forceinline__ void vld_stream(const void* p, size_t i, X (&o)[V], long) { VV::ld(p, i, o); }
-#ifdef IES_NOSTCS
-template <typename VV, typename X, int V> __device__ __forceinline__ void vst_stream(void* p, size_t i, const X (&o)[V], int) { VV::st(p, i, o); }
-#else
 template <typename VV, typename X, int V> __device__ __forceinline__ auto vst_stream(void* p, size_t i, const X (&o)[V], int)
     -> decltype(VV::st_stream(p, i, o)) { VV::st_stream(p, i, o); }
-#endif
 template <typename VV, typename X, int V> __device__ __forceinline__ void vst_stream(void* p, size_t i, const X (&o)[V], long) { VV::st(p, i, o); }
 
 // Coefficients of V consecutive cells: from the palette form (one index byte per cell, the
