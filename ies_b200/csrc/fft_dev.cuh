@@ -226,7 +226,7 @@ template <typename C, int N> struct XchgContig8 {
 };
 // Contiguous lines without padding: element i lives at i ^ ((i >> 4) & 15), which keeps both
 // the radix-16 scatter (16t + m) and the strided gather (t + 16m) conflict free while a line
-// occupies exactly N elements (the alternating-orientation kernel keeps its tile at 64 KB).
+// occupies exactly N elements (k_zline_update keeps its tile at 64 KB).
 template <typename C, int N> struct XchgContigSw {
     C* base;
     static constexpr int LS = N;

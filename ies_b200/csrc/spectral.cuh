@@ -438,7 +438,7 @@ int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
 }
 
 // Strided-line derivative of the pair (A, B): axis 0 = x lines of the whole slab (PSTD),
-// axis 1 = y lines of the x-planes [i0, i1) (refresh of the alternating SHPF path's scratch).
+// axis 1 = y lines of the x-planes [i0, i1).
 template <typename T, bool CPLX>
 int launch_sline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int axis, int i0, int i1) {
     using C = typename Cx<T>::type;
