@@ -423,12 +423,14 @@ struct ies_probe {
         default: set_error("bad dtype"); return 1;                      \
     }
 
-static int dev_alloc(Ctx* c, void** p, size_t bytes, bool zero = true) {
+namespace ies {
+int dev_alloc(Ctx* c, void** p, size_t bytes, bool zero) {
     IES_CUDA(cudaMalloc(p, bytes ? bytes : 1));
     c->owned.push_back(*p);
     if (zero) IES_CUDA(cudaMemsetAsync(*p, 0, bytes, c->stream));
     return 0;
 }
+}  // namespace ies
 
 static int fill_params(ies_ctx* c, int half, UpdParams& p) {
     const int fo = half == IES_HALF_H ? 0 : 3, go = half == IES_HALF_H ? 3 : 0;
@@ -462,6 +464,22 @@ static int ensure_scratch(ies_ctx* c, int first, int last) {
     return 0;
 }
 
+// SHPF with a Bloch / periodic x axis: ghost-plane copies of the DIFFERENTIATED field after
+// the update (_updateH_BBC_SHPF / _updateE_BBC_SHPF, space.py:1898-1912, 2073-2085).
+template <typename T, bool CP>
+static int post_ghost_x(ies_ctx* c, const UpdParams& p) {
+    if (c->cfg.method != IES_SHPF || !c->ghost_on[0]) return 0;
+    if (c->cfg.nx < 4) { set_error("periodic axis needs >= 4 cells"); return 1; }
+    const long tot = (long)c->cfg.ny * c->cfg.nz * 3;
+    k_ghost<T, CP><<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(
+        const_cast<void*>(p.F[0]), const_cast<void*>(p.F[1]), const_cast<void*>(p.F[2]), nullptr, nullptr,
+        c->cfg.nx, c->cfg.ny, c->cfg.nz, 0, make_double2(c->ghost_pp[0][0], c->ghost_pp[0][1]),
+        make_double2(c->ghost_pm[0][0], c->ghost_pm[0][1]));
+    count_launch();
+    IES_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // phase: -1 = whole half-step; 0 = the part that needs no neighbour plane (the z-line and
 // x-line derivative passes), so that a slab's halo exchange can overlap it; 1 = the rest.
 template <typename T, bool CP>
@@ -469,7 +487,9 @@ static int do_update(ies_ctx* c, int half, int phase) {
     UpdParams p;
     if (fill_params(c, half, p)) return 1;
     const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
-    const bool overlap_ok = c->cfg.method != IES_FDTD && !(c->cfg.method == IES_SHPF && c->use_split);
+    const bool fused = c->cfg.method == IES_SHPF && c->use_fused && !CP && c->cfg.ny == c->cfg.nz &&
+                       (c->cfg.ny == 64 || c->cfg.ny == 128 || c->cfg.ny == 256 || c->cfg.ny == 512);
+    const bool overlap_ok = c->cfg.method != IES_FDTD && !fused;
     if (!overlap_ok) { if (phase == 0) return 0; phase = -1; }       // everything in phase 1
     if (c->cfg.method == IES_FDTD) {
         // ghost copies on the differentiated field, axis order x, y, z (space.py:1798-1858)
@@ -507,13 +527,31 @@ static int do_update(ies_ctx* c, int half, int phase) {
     }
     for (int a = 1; a < 3; ++a)
         if (!c->mult[half][a]) { set_error("spectral multiplier not set (malloc()/init_update_constants() missing)"); return 1; }
-    if (ensure_scratch(c, 0, c->cfg.method == IES_PSTD ? 3 : 1)) return 1;
+    {
+        const bool ring_only = fused && c->fused_ring_planes > 0 && c->fused_ring_planes < c->cfg.nx;
+        if (!ring_only && ensure_scratch(c, 0, c->cfg.method == IES_PSTD ? 3 : 1)) return 1;
+    }
     p.dz[0] = c->scratch[0]; p.dz[1] = c->scratch[1];
-    if (c->cfg.method == IES_SHPF && c->use_split) {
-        // G_y (+ d/dz F_y -> scratch) in the z-line kernel, G_x and G_z in the y-line kernel
-        if (launch_zline_update<T, CP>(c, p, half)) return 1;
-        if (launch_yline_update<T, CP>(c, p, half, true)) return 1;
-        return 0;
+    if (fused) {
+        // one launch: z-line tiles run LEAD planes ahead of the y-line update tiles (shpf_fused.cuh)
+        int ring = c->fused_ring_planes;
+        if (ring <= 0 || ring >= c->cfg.nx) ring = c->cfg.nx;
+        if (ring < c->cfg.nx) {
+            if (ring < c->fused_lead + 2) ring = c->fused_lead + 2;
+            if (c->fused_ring_alloc < ring) {
+                const size_t rb = (size_t)ring * ny * nz * c->esize;
+                for (int q = 0; q < 2; ++q) if (dev_alloc(c, &c->fused_ring[q], rb)) return 1;
+                c->fused_ring_alloc = ring;
+            }
+            p.dz[0] = c->fused_ring[0]; p.dz[1] = c->fused_ring[1];
+        }
+        const int keep = c->fused_ring_planes;
+        c->fused_ring_planes = ring;
+        const int rc = launch_shpf_fused<T, CP>(c, p, half);
+        c->fused_ring_planes = keep;
+        if (rc == 1) return 1;
+        if (rc == 0) return post_ghost_x<T, CP>(c, p);
+        p.dz[0] = c->scratch[0]; p.dz[1] = c->scratch[1];       // no instantiation: two-kernel path
     }
     p.dxs[0] = c->scratch[2]; p.dxs[1] = c->scratch[3];
     if (phase != 1) {
@@ -524,7 +562,8 @@ static int do_update(ies_ctx* c, int half, int phase) {
         if (launch_zline<T, CP>(c, p.F[1], p.F[0], c->scratch[0], c->scratch[1], half, 0, nx, 0)) return 1;
     }
     if (phase != 0) {
-        if (launch_yline_update<T, CP>(c, p, half, false)) return 1;
+        if (launch_yline_update<T, CP>(c, p, half)) return 1;
+        if (post_ghost_x<T, CP>(c, p)) return 1;
     }
     return 0;
 }
@@ -575,8 +614,11 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     if (const char* e = getenv("IES_B200_PALETTE")) c->use_palette = atoi(e);
     for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
     // spectral scratch is allocated on first use
-    c->use_split = 0;     // measured: split 3.43 ms/step vs 3.19 (the z-line kernel does not overlap its streaming with the FFT)
-    if (const char* e = getenv("IES_B200_SPLIT")) c->use_split = atoi(e);
+    c->use_fused = 0; c->fused_lead = 3; c->fused_ring_planes = 0; c->fused_ring_alloc = 0;
+    c->fused_ring[0] = c->fused_ring[1] = nullptr; c->fused_sync = nullptr; c->twz_t = nullptr;
+    if (const char* e = getenv("IES_B200_FUSED")) c->use_fused = atoi(e);
+    if (const char* e = getenv("IES_B200_FUSED_LEAD")) c->fused_lead = std::max(1, atoi(e));
+    if (const char* e = getenv("IES_B200_FUSED_RING")) c->fused_ring_planes = atoi(e);
     const size_t pbytes = (size_t)cfg->ny * cfg->nz * c->esize;
     for (int h = 0; h < 2; ++h) for (int w = 0; w < 2; ++w) if (dev_alloc(c, &c->halo_recv[h][w], pbytes)) return 1;
     for (int h = 0; h < 2; ++h) for (int a = 0; a < 3; ++a) c->mult[h][a] = nullptr;
@@ -597,6 +639,31 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
         if (dev_alloc(c, &c->tw[a], b, false)) return 1;
         IES_CUDA(cudaMemcpyAsync(c->tw[a], c->dbl ? (void*)hd.data() : (void*)hf.data(), b, cudaMemcpyHostToDevice, c->stream));
         IES_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    if (cfg->method == IES_SHPF) {
+        // fused half-step: counters, and the z axis' stage tables transposed to [m][jj]
+        // (fft_dev.cuh TwTables: forward stage NS = 16, inverse stage NS = N/16; one table at N = 256)
+        { void* q; if (dev_alloc(c, &q, sizeof(unsigned) * (size_t)(1 + 2 * cfg->nx))) return 1; c->fused_sync = (unsigned*)q; }
+        const int n = cfg->nz;
+        if (n > 16) {
+            const int r1 = (n / 16 >= 16) ? 16 : n / 16, fwd = r1 * 16, nsi = n / 16, fstep = n / (16 * r1);
+            const bool shared = n == 256;
+            const int tot = (shared ? 0 : fwd) + n;
+            std::vector<double> hd(2 * (size_t)tot);
+            std::vector<float> hf(2 * (size_t)tot);
+            auto W = [&](int k, int at) {
+                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)(k & (n - 1)) / (long double)n;
+                hd[2 * at] = (double)cosl(ang); hd[2 * at + 1] = (double)sinl(ang);
+                hf[2 * at] = (float)hd[2 * at]; hf[2 * at + 1] = (float)hd[2 * at + 1];
+            };
+            int at = 0;
+            if (!shared) for (int q = 0; q < fwd; ++q) W((q / 16) * (q % 16) * fstep, at++);
+            for (int q = 0; q < n; ++q) W((q / nsi) * (q % nsi), at++);
+            const size_t b = (size_t)2 * tot * (c->dbl ? 8 : 4);
+            if (dev_alloc(c, &c->twz_t, b, false)) return 1;
+            IES_CUDA(cudaMemcpyAsync(c->twz_t, c->dbl ? (void*)hd.data() : (void*)hf.data(), b, cudaMemcpyHostToDevice, c->stream));
+            IES_CUDA(cudaStreamSynchronize(c->stream));
+        }
     }
     for (int q = 0; q < 6; ++q) {
         c->ubox[q].lo[0] = c->ubox[q].lo[1] = c->ubox[q].lo[2] = 0;
@@ -632,7 +699,9 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     if (n == "palette") c->use_palette = v;
     else if (n == "ctile") c->use_ctile = v;
     else if (n == "fdtd_vec") c->fdtd_vec = v;
-    else if (n == "split") c->use_split = v;
+    else if (n == "fused") c->use_fused = v;
+    else if (n == "fused_lead") c->fused_lead = v < 1 ? 1 : v;
+    else if (n == "fused_ring") c->fused_ring_planes = v;
     else if (n == "reset_psi") {               // zero the CPML auxiliary state (restart a run on new fields)
         for (int h = 0; h < 2; ++h)
             for (const PmlTermDev& t : c->terms[h])

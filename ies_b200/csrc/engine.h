@@ -78,7 +78,13 @@ struct Ctx {
     cudaEvent_t ev_t0, ev_t1;          // ies_timer_start/stop
     int profiling;                     // per-kernel CUDA-event timing on/off
     std::vector<cudaEvent_t> prof_ev[4][2];   // [slot][begin/end]
-    int use_split;                     // SHPF: 1 = split update (shpf_split.cuh), 0 = z-line + full y-line kernels
+    // fused single-launch SHPF half-step (shpf_fused.cuh)
+    int use_fused;                     // 1 = k_shpf_fused where instantiated, 0 = k_zline + k_yline_update
+    int fused_lead, fused_ring_planes; // planes of lead of the z role; scratch ring size in planes
+    unsigned* fused_sync;              // ticket + zdone[nx] + ydone[nx]
+    void* fused_ring[2];               // ring scratch (fused_ring_planes planes each) or null
+    int fused_ring_alloc;              // planes the ring buffers were allocated for
+    void* twz_t;                       // z axis: transposed stage tables [forward | inverse] (fft_dev.cuh TwTables)
 };
 
 enum { PROF_ZLINE = 0, PROF_YLINE_UPDATE = 1, PROF_XLINE = 2, PROF_FDTD = 3 };
@@ -97,9 +103,10 @@ int launch_zline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
 template <typename T, bool CPLX>
 int launch_sline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int half, int axis, int i0, int i1);
 template <typename T, bool CPLX>
-int launch_zline_update(Ctx* c, const UpdParams& p, int half);     // shpf_split.cuh
+int launch_yline_update(Ctx* c, const UpdParams& p, int half);
 template <typename T, bool CPLX>
-int launch_yline_update(Ctx* c, const UpdParams& p, int half, bool split);
+int launch_shpf_fused(Ctx* c, const UpdParams& p, int half);       // shpf_fused.cuh; 2 = not instantiated
+int dev_alloc(Ctx* c, void** p, size_t bytes, bool zero = true);
 
 bool fft_len_supported(int n);
 

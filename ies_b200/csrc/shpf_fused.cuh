@@ -1,0 +1,181 @@
+// SHPF half-step as ONE launch (space.py:709-727 + 801-811 for updateH, 953-970 + 1017-1025
+// for updateE, CPML 1110-1712): the z-line derivative tiles and the y-line update tiles of
+// spectral.cuh run as two ROLES of the same grid, ordered by a ticket so that the z tiles of
+// plane p are handed out LEAD planes ahead of the y tiles that consume them.
+//
+//   ticket t -> group g = t / (ZT + YT), slot r = t % (ZT + YT)
+//      r <  ZT : z role, tile r of plane g            (if g < nx)
+//      r >= ZT : y role, tile r - ZT of plane g - LEAD (if g >= LEAD)
+//
+// Why: the two-kernel path writes the z-derivative scratch (2 arrays) to HBM in one sweep and
+// reads it back a whole sweep later, and reads F_x / F_y once per sweep: 6 of its 15-16 array
+// passes.  Here a scratch plane is consumed a few planes after it was produced, from a RING of
+// `ring` planes that stays in the 126 MB L2, and the second reads of F_x / F_y hit L2 as well.
+//
+// Ordering: zdone[p] / ydone[p] count the finished tiles of plane p (the launcher zeroes the
+// counters and the ticket in stream order before every launch).  A y tile waits for
+// zdone[plane] after its own FFT phase; a z tile waits for ydone[plane - ring] before it
+// overwrites a ring slot.  Both waits are on tickets handed out EARLIER (ring > LEAD), and a
+// ticket is drawn by a CTA that is already resident, so every wait is on a running or finished
+// CTA: no deadlock whatever the hardware's block scheduling order is.
+//
+// Arithmetic is the same expression on the same operands as in k_zline + k_yline_update, so the
+// fields are bit-identical to the two-kernel path.
+#pragma once
+#include "spectral.cuh"
+
+namespace ies {
+
+struct FusedParams {
+    unsigned* ticket;           // one counter
+    unsigned* zdone;            // [nx]
+    unsigned* ydone;            // [nx]
+    int lead;                   // planes the z role runs ahead of the y role
+    int ring;                   // scratch planes (ring > lead; ring >= nx: no wrap)
+    int zt, yt;                 // tiles per plane of each role
+};
+
+__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target) {
+    if (threadIdx.x == 0) {
+        while (*(volatile const unsigned*)ctr < target) __nanosleep(100);
+        __threadfence();        // acquire: also drops this SM's stale L1 lines of a reused ring slot
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void signal_counter(unsigned* ctr) {
+    __syncthreads();            // every thread's stores / loads of the tile are issued
+    if (threadIdx.x == 0) {
+        __threadfence();        // release (cumulative over the CTA through the barrier)
+        atomicAdd(ctr, 1u);
+    }
+}
+
+// z role: LPB adjacent z lines of plane pz -> ring slot.  Same transform as k_zline; the
+// exchange buffer is the unpadded swizzled one (64 KB like the y role's stash) and the stage
+// tables come transposed from global memory (twt = [forward stage | inverse stage]).
+template <typename T, bool CPLX, int N>
+__device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedParams& fp, const int pz, const int tile,
+                                             typename Cx<T>::type* xbuf,
+                                             const typename Cx<T>::type* __restrict__ tw,
+                                             const typename Cx<T>::type* __restrict__ twt,
+                                             const typename Cx<T>::type* __restrict__ ml) {
+    using C = typename Cx<T>::type;
+    using F = Fld<T, CPLX>;
+    using X = XchgContigSw<C, N>;
+    using TT_ = TwTables<N, 16>;
+    constexpr bool TWT = N > 16;
+    constexpr int TT = ZCfg<N, 16>::TT, LPB = ZCfg<N, 16>::LPB;
+    const C* twf = twt;
+    const C* twi = TT_::SHARED ? twt : twt + TT_::FWD;
+    const int t = threadIdx.x % TT, l = threadIdx.x / TT;
+    const int row = tile * LPB + l;
+    const bool ok = row < p.ny;
+    const size_t ibase = ((size_t)pz * p.ny + row) * N;
+    const size_t obase = ((size_t)(pz % fp.ring) * p.ny + row) * N;
+    X xb{xbuf + (size_t)l * X::LS};
+    C v[F::NF][16];
+#pragma unroll
+    for (int f = 0; f < F::NF; ++f) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            if (ok) v[f][q] = F::ld(p.F[1], p.F[0], ibase + line_index_v<N, 16>(t, q), f);
+            else { v[f][q].x = 0; v[f][q].y = 0; }
+        }
+        fft_forward_v<N, 16, TWT>(v[f], t, tw, xb, twf);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[f][q] = cmul(v[f][q], ml[spec_index_v<N, 16>(t, q)]);
+        fft_inverse_v<N, 16, TWT>(v[f], t, tw, xb, twi);
+    }
+    // the slot's previous tenant (plane pz - ring) must have been consumed
+    if (pz - fp.ring >= p.i0) wait_counter(fp.ydone + (pz - fp.ring), (unsigned)fp.yt);
+    if (ok) {
+        void* dA = const_cast<void*>(p.dz[0]);
+        void* dB = const_cast<void*>(p.dz[1]);
+#pragma unroll
+        for (int f = 0; f < F::NF; ++f) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) F::st(dA, dB, obase + line_index_v<N, 16>(t, q), v[f][q], f);
+        }
+    }
+    signal_counter(fp.zdone + pz);
+}
+
+template <typename T, bool CPLX, int NY, int NZ, bool PAL>
+__global__ void __launch_bounds__(256, 2)
+k_shpf_fused(const UpdParams p, const FusedParams fp,
+             const typename Cx<T>::type* __restrict__ twy, const typename Cx<T>::type* __restrict__ mly,
+             const typename Cx<T>::type* __restrict__ twz, const typename Cx<T>::type* __restrict__ twzt,
+             const typename Cx<T>::type* __restrict__ mlz) {
+    using C = typename Cx<T>::type;
+    static_assert(!CPLX, "fused SHPF kernel: real field dtypes (complex tiles are 128 threads wide)");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* xbuf = reinterpret_cast<C*>(smem_raw);
+    __shared__ unsigned s_ticket;
+    if (threadIdx.x == 0) {
+        s_ticket = atomicAdd(fp.ticket, 1u);
+    }
+    __syncthreads();
+    const int per = fp.zt + fp.yt;
+    const int g = (int)(s_ticket / (unsigned)per), r = (int)(s_ticket % (unsigned)per);
+    const int nplanes = p.i1 - p.i0;
+    if (r < fp.zt) {
+        if (g >= nplanes) return;
+        fused_z_role<T, CPLX, NZ>(p, fp, p.i0 + g, r, xbuf, twz, twzt, mlz);
+    } else {
+        const int py = g - fp.lead;
+        if (py < 0) return;
+        const int i = p.i0 + py;
+        const int kb = r - fp.zt;
+        yline_phase_a<T, CPLX, NY>(p, i, kb * YCfg<T, CPLX, NY>::W, xbuf, twy, mly);
+        wait_counter(fp.zdone + i, (unsigned)fp.zt);     // also the barrier that publishes the stash
+        const long long plane = (long long)p.ny * p.nz;
+        const long long dz_off = ((long long)(i % fp.ring) - (long long)i) * plane;
+        yline_phase_b_dispatch<T, CPLX, NY, PAL>(p, i, kb, fp.yt, xbuf, dz_off);
+        signal_counter(fp.ydone + i);
+    }
+}
+
+// Host side: launch the fused half-step on planes [p.i0, p.i1).  Returns 0 / 1 like the other
+// launchers, 2 when this (dtype, ny, nz) has no fused instantiation (caller takes the two-kernel path).
+template <typename T, bool CPLX>
+int launch_shpf_fused(Ctx* c, const UpdParams& p, int half) {
+    if constexpr (CPLX) { return 2; }
+    else {
+        using C = typename Cx<T>::type;
+        const int ny = c->cfg.ny, nz = c->cfg.nz;
+        if (ny != nz) return 2;
+        if (p.i1 <= p.i0) return 0;
+        const bool pal = p.Cidx != nullptr;
+        FusedParams fp;
+        fp.ticket = c->fused_sync; fp.zdone = c->fused_sync + 1; fp.ydone = c->fused_sync + 1 + c->cfg.nx;
+        fp.lead = c->fused_lead;
+        fp.ring = c->fused_ring_planes;
+        IES_CUDA(cudaMemsetAsync(c->fused_sync, 0, sizeof(unsigned) * (size_t)(1 + 2 * c->cfg.nx), c->stream));
+        const int nplanes = p.i1 - p.i0;
+#define F_CASE(NN) {                                                                        \
+            fp.zt = (ny + ZCfg<NN, 16>::LPB - 1) / ZCfg<NN, 16>::LPB;                       \
+            fp.yt = (nz + YCfg<T, CPLX, NN>::W - 1) / YCfg<T, CPLX, NN>::W;                  \
+            const size_t sm = sizeof(C) * (size_t)NN * YCfg<T, CPLX, NN>::W;                 \
+            auto kern = pal ? k_shpf_fused<T, CPLX, NN, NN, true> : k_shpf_fused<T, CPLX, NN, NN, false>; \
+            if (set_smem(kern, sm)) return 1;                                               \
+            const unsigned grid = (unsigned)((nplanes + fp.lead) * (fp.zt + fp.yt));        \
+            kern<<<grid, 256, sm, c->stream>>>(p, fp, (const C*)c->tw[1], (const C*)c->mult[half][1], \
+                (const C*)c->tw[2], (const C*)c->twz_t, (const C*)c->mult[half][2]);        \
+        }
+        prof_mark(c, PROF_YLINE_UPDATE, 0);
+        switch (ny) {
+            case 64: F_CASE(64); break;
+            case 128: F_CASE(128); break;
+            case 256: F_CASE(256); break;
+            case 512: F_CASE(512); break;
+            default: return 2;
+        }
+        prof_mark(c, PROF_YLINE_UPDATE, 1);
+#undef F_CASE
+        count_launch();
+        IES_CUDA(cudaGetLastError());
+        return 0;
+    }
+}
+
+}  // namespace ies

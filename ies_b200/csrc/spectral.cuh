@@ -185,14 +185,15 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 // ------------------------------------------ y lines + fused field update -----
 // Phase B of k_yline_update.  FAST: no CPML term touches the tile and every update box either
 // contains or misses it (upd = component mask, CTA-uniform): straight-line interior code.
-// SPLIT (SHPF): the z-line kernel has already updated G_y and left d/dz F_y in dz[0]; this
-// kernel updates G_x and G_z only (k_zline_update below).
 // CM: where the coefficient comes from -- 0 the f64 array, 1 the palette form, 2 one value for
 // the whole tile (cuni; materials are piecewise constant, so most tiles are uniform and skip the
 // coefficient array altogether: one array pass less for the HBM-bound kernel).
-template <typename T, bool CPLX, int N, int CM, bool FAST, bool SPLIT>
+// dz_off: element offset of the z-derivative scratch relative to the field index (0 for the
+// full-size scratch of the two-kernel path, the ring slot offset in the fused kernel).
+template <typename T, bool CPLX, int N, int CM, bool FAST>
 __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, const int k0, const unsigned mask,
-                                              const int upd, const typename Cx<T>::type* xbuf, const double cuni) {
+                                              const int upd, const typename Cx<T>::type* xbuf, const double cuni,
+                                              const long long dz_off) {
     using C = typename Cx<T>::type;
     using A = typename AccT<CPLX>::type;
     using VV = Vec<T, CPLX>;
@@ -225,29 +226,20 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
         for (int u = 0; u < PB; ++u) {
             const int j = tr + (pass0 + u) * RP;
             const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
-            VV::ld(p.dz[0], (size_t)((long long)idx + p.dz_off), dz0[u]);
-            if constexpr (SPLIT) {
-                if (nb_any) {
-                    VV::ld(nFy, nbase + (size_t)j * p.nz + k, a4[u]);
-                    VV::ld(p.F[1], idx, b4[u]);
-                }
-                VV::ld(p.G[0], idx, g[u][0]);
-                VV::ld(p.G[2], idx, g[u][2]);
-            } else {
-                VV::ld(p.dz[1], (size_t)((long long)idx + p.dz_off), dz1[u]);
-                if (p.pstd) {
-                    VV::ld(p.dxs[0], idx, a3[u]);
-                    VV::ld(p.dxs[1], idx, a4[u]);
-                } else if (nb_any) {
-                    const size_t nidx = nbase + (size_t)j * p.nz + k;
-                    VV::ld(nFz, nidx, a3[u]);
-                    VV::ld(nFy, nidx, a4[u]);
-                    VV::ld(p.F[2], idx, b3[u]);
-                    VV::ld(p.F[1], idx, b4[u]);
-                }
-#pragma unroll
-                for (int c = 0; c < 3; ++c) VV::ld(p.G[c], idx, g[u][c]);
+            VV::ld(p.dz[0], (size_t)((long long)idx + dz_off), dz0[u]);
+            VV::ld(p.dz[1], (size_t)((long long)idx + dz_off), dz1[u]);
+            if (p.pstd) {
+                VV::ld(p.dxs[0], idx, a3[u]);
+                VV::ld(p.dxs[1], idx, a4[u]);
+            } else if (nb_any) {
+                const size_t nidx = nbase + (size_t)j * p.nz + k;
+                VV::ld(nFz, nidx, a3[u]);
+                VV::ld(nFy, nidx, a4[u]);
+                VV::ld(p.F[2], idx, b3[u]);
+                VV::ld(p.F[1], idx, b4[u]);
             }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) VV::ld(p.G[c], idx, g[u][c]);
             if constexpr (CM == 2) {
 #pragma unroll
                 for (int v = 0; v < V; ++v) cf[u][v] = cuni;
@@ -275,25 +267,16 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
                         d[0] = (double)r0.x; d[5] = (double)r0.y;
                     }
                     d[1] = dz0[u][v];
-                    if constexpr (SPLIT) {
-                        d[2] = a_zero(A()); d[3] = a_zero(A());
-                        d[4] = nb_any ? a_scale(sx, a_sub(a4[u][v], b4[u][v])) : a_zero(A());
-                        A gg[3] = {g[u][0][v], a_zero(A()), g[u][2][v]};
-                        if constexpr (FR) cell_update_fast<CPLX, 5>(upd, cf[u][v], d, gg);
-                        else cell_update_regs<T, CPLX, 5>(p, bmask, i, j, k + v, cf[u][v], d, gg);
-                        g[u][0][v] = gg[0]; g[u][2][v] = gg[2];
-                    } else {
-                        d[2] = dz1[u][v];
-                        if (p.pstd) { d[3] = a3[u][v]; d[4] = a4[u][v]; }
-                        else if (nb_any) {
-                            d[3] = a_scale(sx, a_sub(a3[u][v], b3[u][v]));
-                            d[4] = a_scale(sx, a_sub(a4[u][v], b4[u][v]));
-                        } else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
-                        A gg[3] = {g[u][0][v], g[u][1][v], g[u][2][v]};
-                        if constexpr (FR) cell_update_fast<CPLX>(upd, cf[u][v], d, gg);
-                        else cell_update_regs<T, CPLX>(p, bmask, i, j, k + v, cf[u][v], d, gg);
-                        g[u][0][v] = gg[0]; g[u][1][v] = gg[1]; g[u][2][v] = gg[2];
-                    }
+                    d[2] = dz1[u][v];
+                    if (p.pstd) { d[3] = a3[u][v]; d[4] = a4[u][v]; }
+                    else if (nb_any) {
+                        d[3] = a_scale(sx, a_sub(a3[u][v], b3[u][v]));
+                        d[4] = a_scale(sx, a_sub(a4[u][v], b4[u][v]));
+                    } else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
+                    A gg[3] = {g[u][0][v], g[u][1][v], g[u][2][v]};
+                    if constexpr (FR) cell_update_fast<CPLX>(upd, cf[u][v], d, gg);
+                    else cell_update_regs<T, CPLX>(p, bmask, i, j, k + v, cf[u][v], d, gg);
+                    g[u][0][v] = gg[0]; g[u][1][v] = gg[1]; g[u][2][v] = gg[2];
                 }
             }
         };
@@ -310,13 +293,8 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
             // streaming stores (st.global.cs, evict-first): the updated field is not touched again
             // in this half-step; measured 1.29 -> 1.14 ms per launch (loads stay allocating:
             // ld.cs / L1::no_allocate / ld.cg on the streaming operands cost 8-13 %)
-            if constexpr (SPLIT) {
-                vst_stream<VV>(p.G[0], idx, g[u][0], 0);
-                vst_stream<VV>(p.G[2], idx, g[u][2], 0);
-            } else {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) vst_stream<VV>(p.G[c], idx, g[u][c], 0);
-            }
+            for (int c = 0; c < 3; ++c) vst_stream<VV>(p.G[c], idx, g[u][c], 0);
         }
     }
 }
@@ -327,63 +305,75 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
 // Phase B: the CTA re-maps to 16-byte vectors along z (V cells per thread) and streams
 //          the cell update: PB row groups of loads are issued before any arithmetic so
 //          enough bytes are in flight to cover HBM latency.
-// One CTA = the tile (plane i, columns kb*W .. kb*W+W-1, all rows).  PAL: coefficients come
+// One CTA = the tile (plane i, columns k0 .. k0+W-1, all rows).  PAL: coefficients come
 // from the palette form (update_dev.cuh ld_coeff).
-template <typename T, bool CPLX, int N, bool PAL, bool SPLIT>
+// The twiddle / multiplier tables are read straight from global memory (L1-resident,
+// 8 KB): that keeps the CTA at N*W*16 B of shared memory, so two CTAs fit the 132 KB
+// carve-out and 96 KB of L1 remain for loads in flight (measured: the kernel's
+// bandwidth follows the L1 size left by the carve-out).
+template <typename T, bool CPLX, int N>
+__device__ __forceinline__ void yline_phase_a(const UpdParams& p, const int i, const int k0,
+                                              typename Cx<T>::type* xbuf,
+                                              const typename Cx<T>::type* __restrict__ tw,
+                                              const typename Cx<T>::type* __restrict__ ml) {
+    using C = typename Cx<T>::type;
+    using F = Fld<T, CPLX>;
+    using S = YCfg<T, CPLX, N>;
+    constexpr int W = S::W;
+    constexpr int NF = F::NF;
+    const size_t plane = (size_t)p.ny * p.nz;
+    const int c = threadIdx.x % W, t = threadIdx.x / W;
+    const int k = k0 + c;
+    const bool ok = k < p.nz;
+    const size_t pbase = (size_t)i * plane + k;
+    // pair (F_z, F_x): Re -> d/dy F_z (slot 0), Im -> d/dy F_x (slot 5)
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+        XchgStrided<C, W> xb{xbuf + (size_t)f * N * W + c};
+        C v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            if (ok) v[q] = F::ld(p.F[2], p.F[0], pbase + (size_t)line_index<N>(t, q) * p.nz, f);
+            else { v[q].x = 0; v[q].y = 0; }
+        }
+        fft_forward<N>(v, t, tw, xb);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], ml[spec_index<N>(t, q)]);
+        fft_inverse<N>(v, t, tw, xb);
+        __syncthreads();                 // everyone finished reading the exchange buffer
+#pragma unroll
+        for (int q = 0; q < 16; ++q) xb.st(line_index<N>(t, q), v[q]);
+    }
+}
+
+// phase B for the tile (plane i, column block kb of ntk): picks the straight-line / uniform-
+// coefficient variants per tile.
+template <typename T, bool CPLX, int N, bool PAL>
+__device__ __forceinline__ void yline_phase_b_dispatch(const UpdParams& p, const int i, const int kb, const int ntk,
+                                                       const typename Cx<T>::type* xbuf, const long long dz_off) {
+    constexpr int W = YCfg<T, CPLX, N>::W;
+    const int k0 = kb * W;
+    const unsigned mask = term_mask(p, i, i + 1, 0, p.ny, k0, k0 + W);
+    const int upd = tile_update_class(p, i, i + 1, 0, p.ny, k0, min(k0 + W, p.nz));
+    // per-tile uniform coefficient (engine.cu: k_tile_uniform), NaN when the tile is not uniform
+    const double cuni = p.Ctile ? p.Ctile[(size_t)i * ntk + kb] : __longlong_as_double(0x7ff8000000000000LL);
+    const bool fast = mask == 0u && upd >= 0;
+    if (fast && cuni == cuni) yline_phase_b<T, CPLX, N, 2, true>(p, i, k0, mask, upd, xbuf, cuni, dz_off);
+    else if (fast) yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), true>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
+    else yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), false>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
+}
+
+template <typename T, bool CPLX, int N, bool PAL>
 __global__ void __launch_bounds__(YCfg<T, CPLX, N>::THREADS, YCfg<T, CPLX, N>::MINB)
 k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
                const typename Cx<T>::type* __restrict__ ml) {
     using C = typename Cx<T>::type;
-    using F = Fld<T, CPLX>;
-    using A = typename AccT<CPLX>::type;
-    using VV = Vec<T, CPLX>;
-    using S = YCfg<T, CPLX, N>;
-    constexpr int W = S::W;
-    constexpr int V = VV::V;
-    constexpr int NF = F::NF;
-    // The twiddle / multiplier tables are read straight from global memory (L1-resident,
-    // 8 KB): that keeps the CTA at N*W*16 B of shared memory, so two CTAs fit the 132 KB
-    // carve-out and 96 KB of L1 remain for loads in flight (measured: the kernel's
-    // bandwidth follows the L1 size left by the carve-out).
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* xbuf = reinterpret_cast<C*>(smem_raw);      // NF buffers of N*W: exchange, then derivative stash
     const int i = p.i0 + (int)blockIdx.y;
-    const int k0 = (int)blockIdx.x * W;
-    const size_t plane = (size_t)p.ny * p.nz;
-    {
-        const int c = threadIdx.x % W, t = threadIdx.x / W;
-        const int k = k0 + c;
-        const bool ok = k < p.nz;
-        const size_t pbase = (size_t)i * plane + k;
-        // pair (F_z, F_x): Re -> d/dy F_z (slot 0), Im -> d/dy F_x (slot 5)
-#pragma unroll
-        for (int f = 0; f < NF; ++f) {
-            XchgStrided<C, W> xb{xbuf + (size_t)f * N * W + c};
-            C v[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                if (ok) v[q] = F::ld(p.F[2], p.F[0], pbase + (size_t)line_index<N>(t, q) * p.nz, f);
-                else { v[q].x = 0; v[q].y = 0; }
-            }
-            fft_forward<N>(v, t, tw, xb);
-#pragma unroll
-            for (int q = 0; q < 16; ++q) v[q] = cmul(v[q], ml[spec_index<N>(t, q)]);
-            fft_inverse<N>(v, t, tw, xb);
-            __syncthreads();                 // everyone finished reading the exchange buffer
-#pragma unroll
-            for (int q = 0; q < 16; ++q) xb.st(line_index<N>(t, q), v[q]);
-        }
-        __syncthreads();
-    }
-    // ---------------- phase B: vectorised streaming update ----------------
-    const unsigned mask = term_mask(p, i, i + 1, 0, p.ny, k0, k0 + W);
-    const int upd = tile_update_class(p, i, i + 1, 0, p.ny, k0, min(k0 + W, p.nz));
-    // per-tile uniform coefficient (engine.cu: k_tile_uniform), NaN when the tile is not uniform
-    const double cuni = p.Ctile ? p.Ctile[(size_t)i * gridDim.x + blockIdx.x] : __longlong_as_double(0x7ff8000000000000LL);
-    const bool fast = mask == 0u && upd >= 0;
-    if (fast && cuni == cuni) yline_phase_b<T, CPLX, N, 2, true, SPLIT>(p, i, k0, mask, upd, xbuf, cuni);
-    else if (fast) yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), true, SPLIT>(p, i, k0, mask, upd, xbuf, 0.0);
-    else yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), false, SPLIT>(p, i, k0, mask, upd, xbuf, 0.0);
+    yline_phase_a<T, CPLX, N>(p, i, (int)blockIdx.x * YCfg<T, CPLX, N>::W, xbuf, tw, ml);
+    __syncthreads();
+    yline_phase_b_dispatch<T, CPLX, N, PAL>(p, i, (int)blockIdx.x, (int)gridDim.x, xbuf, p.dz_off);
 }
 
 // ------------------------------------------------------------- launchers -----
@@ -473,7 +463,7 @@ int launch_sline(Ctx* c, const void* A, const void* B, void* dA, void* dB, int h
 }
 
 template <typename T, bool CPLX>
-int launch_yline_update(Ctx* c, const UpdParams& p, int half, bool split) {
+int launch_yline_update(Ctx* c, const UpdParams& p, int half) {
     using C = typename Cx<T>::type;
     const int n = c->cfg.ny;
     if (p.i1 <= p.i0) return 0;
@@ -481,8 +471,7 @@ int launch_yline_update(Ctx* c, const UpdParams& p, int half, bool split) {
 #define Y_CASE(NN) {                                                                        \
         using S = YCfg<T, CPLX, NN>;                                                        \
         size_t sm = sizeof(C) * ((size_t)NN * S::W * Fld<T, CPLX>::NF);                     \
-        auto kern = split ? (pal ? k_yline_update<T, CPLX, NN, true, true> : k_yline_update<T, CPLX, NN, false, true>) \
-                          : (pal ? k_yline_update<T, CPLX, NN, true, false> : k_yline_update<T, CPLX, NN, false, false>); \
+        auto kern = pal ? k_yline_update<T, CPLX, NN, true> : k_yline_update<T, CPLX, NN, false>; \
         if (set_smem(kern, sm)) return 1;                                                   \
         dim3 grid((unsigned)((c->cfg.nz + S::W - 1) / S::W), (unsigned)(p.i1 - p.i0));      \
         kern<<<grid, S::THREADS, sm, c->stream>>>(p, (const C*)c->tw[1],                     \

@@ -1,8 +1,7 @@
 // Explicit instantiation of the spectral kernels for field dtype f64.
-#include "shpf_split.cuh"
+#include "spectral.cuh"
 namespace ies {
 template int launch_zline<double, false>(Ctx*, const void*, const void*, void*, void*, int, int, int, int, cudaStream_t);
 template int launch_sline<double, false>(Ctx*, const void*, const void*, void*, void*, int, int, int, int);
-template int launch_zline_update<double, false>(Ctx*, const UpdParams&, int);
-template int launch_yline_update<double, false>(Ctx*, const UpdParams&, int, bool);
+template int launch_yline_update<double, false>(Ctx*, const UpdParams&, int);
 }  // namespace ies

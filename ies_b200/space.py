@@ -543,7 +543,9 @@ class Basic3D:
     def _full_multiplier(self, ik, shift, kB, n):
         """Full-spectrum multiplier (ik - i kB) * shift; Hermitian extension of the rfft
         table for real fields (irfftn ignores Im of the DC and Nyquist bins)."""
-        m = (ik.ravel().astype(np.complex128) * shift.ravel().astype(np.complex128))
+        # the reference forms iky*ypshift in mmtdtype before it meets the spectrum
+        # (space.py:709-718): round the product there, then widen
+        m = (ik.ravel() * shift.ravel()).astype(self.mmtdtype).astype(np.complex128)
         if kB:
             m = m - 1j * kB * shift.ravel().astype(np.complex128)
         if np.dtype(self.field_dtype).kind == 'c':
@@ -588,6 +590,25 @@ class Basic3D:
                     full = self._full_multiplier(ik, shift, kB, n)
                     buf = np.ascontiguousarray(full).view(np.float64)
                     _lib.check(lib.ies_set_multiplier(self._ctx, half, ax, _lib.dptr(buf), n))
+            # SHPF, x axis: ghost-plane copies of the differentiated field after each update when
+            # apply_BBC was called with a True entry (space.py:1898-1912, 2073-2085)
+            gx = None
+            if self.method == 'SHPF' and self.BBC_called:
+                if bbc[0] == True:
+                    gx = self.Lx - 2 * self.dx
+                elif pbc[0] == True:
+                    gx = 0.
+            if gx is not None:
+                if bbc[1] == True or bbc[2] == True:
+                    # the reference evaluates the y/z Bloch terms on the fields AFTER the x ghost
+                    # copies (space.py:1898-1930); the fused multiplier sees them before
+                    raise NotImplementedError("SHPF: Bloch/periodic x axis together with a Bloch y or z axis")
+                if self.mmt is None:
+                    raise AttributeError("Bloch boundary needs a source.Setter (space.mmt) first")
+                pp, pm = np.exp(+1j * self.mmt[0] * gx), np.exp(-1j * self.mmt[0] * gx)
+                _lib.check(lib.ies_set_ghost(self._ctx, 0, 1, pp.real, pp.imag, pm.real, pm.imag))
+            else:
+                _lib.check(lib.ies_set_ghost(self._ctx, 0, 0, 1., 0., 1., 0.))
         else:
             # FDTD ghost-plane copies (space.py:1798-1858, 1981-2033)
             L = (self.Lx, self.Ly, self.Lz)

@@ -202,6 +202,16 @@ class OracleSpace:
                 for r in halo:
                     r[ix2(0)] = r[ix2(-2)] * pm
 
+    def _ghost_x(self, F3, newL):
+        """_exchange_BBCx with mpi=False (space.py:1714-1727): F[-1] = F[1] e^{+ikL'},
+        F[0] = F[-2] e^{-ikL'} on the three components."""
+        k = self.mmt[0]
+        pp, pm = np.exp(+1j * k * newL), np.exp(-1j * k * newL)
+        for f in F3:
+            f[-1] = f[1] * pp
+        for f in F3:
+            f[0] = f[-2] * pm
+
     # ---------------------------------------------------------------- updateH
     def update_h(self, tstep, halo_E=None):
         """space.py:639-840.  halo_E = (Ey[0], Ez[0]) of rank+1 or None."""
@@ -278,7 +288,17 @@ class OracleSpace:
         """space.py:1893-1950."""
         dt, mu, mm = self.dt, self.mu, self.mmt
         if self.method == 'SHPF':
-            s2 = slice(None, -1)
+            # x axis: ghost-plane copies of E after the H update (space.py:1898-1912;
+            # both branches are plain `if`s there)
+            if self.bbc['x']:
+                self._ghost_x((self.Ex, self.Ey, self.Ez), self.Lx - 2 * self.dx)
+            if self.pbc['x']:
+                self._ghost_x((self.Ex, self.Ey, self.Ez), 0)
+            # [:-1] on the last rank; a rank with a successor has updated its plane
+            # myNx-1 from the halo, and the partition-invariant result (== single rank)
+            # needs the Bloch term there too.  The reference applies [:-1] on EVERY rank
+            # (space.py:1896), a slab-edge quirk of the same kind as Q3 -- waived.
+            s2 = slice(None, -1) if self.rank == self.size - 1 else slice(None)
             if self.bbc['y']:
                 ez = self._spec(self.Ez, self.ypshift, 1)
                 ex = self._spec(self.Ex, self.ypshift, 1)
@@ -374,7 +394,12 @@ class OracleSpace:
         """space.py:2068-2122."""
         dt, eps, mm = self.dt, self.eps, self.mmt
         if self.method == 'SHPF':
-            s2 = slice(1, None)
+            # x axis: ghost-plane copies of H after the E update (space.py:2073-2085, if / elif)
+            if self.bbc['x']:
+                self._ghost_x((self.Hx, self.Hy, self.Hz), self.Lx - 2 * self.dx)
+            elif self.pbc['x']:
+                self._ghost_x((self.Hx, self.Hy, self.Hz), 0)
+            s2 = slice(1, None) if self.rank == 0 else slice(None)      # see _bloch_h
             if self.bbc['y']:
                 hz = self._spec(self.Hz, self.ymshift, 1)
                 hx = self._spec(self.Hx, self.ymshift, 1)

@@ -2,8 +2,9 @@
 
 Run in the build container only (needs /root/reference):
 
-    python -m oracle.pin_against_reference            # all cases
+    python -m oracle.pin_against_reference            # all small golden cases
     python -m oracle.pin_against_reference shpf_f64_xpml
+    python -m oracle.pin_against_reference --digest   # the large DIGEST_CASES (minutes)
 
 For every case in oracle/cases.py it runs the unmodified reference modules
 (oracle/ref_shims.py: cupy->numpy alias, fake mpi4py; N-rank cases on N threads)
@@ -33,6 +34,7 @@ def run_reference(case):
         for t in range(case['steps']):
             C.step_api(sp, setter, case, t)
         return {n: np.asarray(getattr(sp, n)) for n in C.FIELDS}
+    assert not case.get('probe')
 
     outs = R.run_ranks(case['ranks'], work)
     return {n: np.concatenate([o[n] for o in outs], axis=0) for n in C.FIELDS}
@@ -40,14 +42,33 @@ def run_reference(case):
 
 def main(argv):
     os.makedirs(GOLD, exist_ok=True)
-    names = argv or [k['name'] for k in C.CASES]
-    report = {}
+    os.makedirs(os.path.join(GOLD, 'digest'), exist_ok=True)
+    if argv and argv[0] == '--digest':
+        names = argv[1:] or [k['name'] for k in C.DIGEST_CASES]
+    else:
+        names = argv or [k['name'] for k in C.CASES]
+    digest_names = {k['name'] for k in C.DIGEST_CASES}
+    rep_path = os.path.join(GOLD, 'pin_report.json')
+    report = json.load(open(rep_path)) if os.path.exists(rep_path) else {}
     worst = 0.0
     for name in names:
         case = C.CASES_BY_NAME[name]
         ref = run_reference(case)
         ora = C.run_oracle(case)
-        errs = {n: C.rel_l2(ora[n], ref[n]) for n in C.FIELDS}
+        if case.get('nrank_quirk'):
+            # the reference's own N-rank run deviates from its single-rank run on the slab-edge
+            # planes (waived quirk): the oracle is pinned to the SINGLE-rank golden instead
+            base = np.load(os.path.join(GOLD, case['golden'] + '.npz'))
+            dev = max(C.rel_l2(ref[n], base[n]) for n in C.FIELDS)
+            e = max(C.rel_l2(ora[n], base[n]) for n in C.FIELDS)
+            status = 'OK' if e <= 1e-13 else 'FAIL'
+            print(f"{name:28s} oracle(N rank) vs 1-rank golden {e:.3e}  {status}; reference(N rank) vs 1-rank golden {dev:.3e} (waived)")
+            report[name] = dict(oracle_vs_single_rank_golden=e, reference_nrank_vs_single_rank=dev, status=status)
+            worst = max(worst, e / 1e-13)
+            continue
+        errs = C.group_rel_l2(ora, ref) if name in digest_names else {n: C.rel_l2(ora[n], ref[n]) for n in C.FIELDS}
+        if 'probe' in ref:
+            errs['probe'] = C.rel_l2(ora['probe'], ref['probe'])
         amax = max(float(np.abs(ref[n]).max()) for n in C.FIELDS)
         e = max(errs.values())
         # Q3: the reference's slab-edge coefficient quirk makes N-rank != 1-rank when an
@@ -60,6 +81,9 @@ def main(argv):
         print(f"{name:28s} max rel-L2 {e:.3e}  (|field|max {amax:.3e})  {status}")
         report[name] = dict(rel_l2=errs, field_absmax=amax, bound=bound, status=status)
         worst = max(worst, e / bound)
+        if name in digest_names:
+            np.savez_compressed(os.path.join(GOLD, 'digest', name + '.npz'), **C.digest(ref, case))
+            continue
         if case['golden'] != name:
             # N-rank reference run must equal the single-rank golden bit for bit
             base = np.load(os.path.join(GOLD, case['golden'] + '.npz'))

@@ -13,6 +13,11 @@ def load_golden(case):
     return {n: z[n] for n in C.FIELDS}
 
 
+def load_digest(case):
+    z = np.load(os.path.join(GOLD, 'digest', case['golden'] + '.npz'))
+    return {n: z[n] for n in z.files}
+
+
 def tolerance(case):
     """north_star: relative L2 <= 1e-10 in fp64, <= 1e-4 in fp32."""
     return 1e-4 if np.dtype(case['dtype']) in (np.dtype('float32'), np.dtype('complex64')) else 1e-10
@@ -40,6 +45,8 @@ def run_product(ns, case):
         setters.append(ns.source.Setter(sp, s0, s1, case['mmt']))
         for (b0, b1, er, mr) in C.box_list(case):
             ns.structure.Box('box', sp, b0, b1, er, mr)
+        if C.sphere_spec(case) is not None:
+            ns.structure.Sphere('sphere', sp, *C.sphere_spec(case))
         sp.init_update_constants()
         spaces.append(sp)
     for t in range(case['steps']):
@@ -51,12 +58,4 @@ def run_product(ns, case):
 
 
 def worst_rel_l2(got, want):
-    # normalise by the largest field norm of the same kind so that components that are
-    # identically ~0 (e.g. Ex of an x-propagating plane wave) do not divide by zero
-    out = {}
-    for grp in (('Ex', 'Ey', 'Ez'), ('Hx', 'Hy', 'Hz')):
-        den = max(np.linalg.norm(np.asarray(want[n]).ravel()) for n in grp)
-        for n in grp:
-            num = np.linalg.norm((np.asarray(got[n]) - np.asarray(want[n])).ravel())
-            out[n] = float(num / den) if den > 0 else float(num)
-    return out
+    return C.group_rel_l2(got, want)

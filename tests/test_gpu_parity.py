@@ -36,24 +36,53 @@ def test_case_vs_oracle_live(product, name):
     assert max(errs.values()) <= H.tolerance(case), (name, errs)
 
 
-SPLIT_CASES = ['shpf_f64_xpml', 'shpf_f32_xpml', 'shpf_c64_xpml', 'shpf_c128_bloch_yz', 'shpf_f64_allpml_r2',
-               'shpf_f64_ypml_only', 'shpf_f64_xpml_64', 'shpf_f32_allpml_64', 'shpf_c128_bloch_yz_128',
-               'shpf_f64_xpml_16x64', 'shpf_f64_src_ez', 'shpf_f64_src_ex_hard', 'shpf_f64_src_hy_r2',
-               'shpf_c128_src_hx_bloch', 'shpf_f32_src_ez_plane']
-
-
-@pytest.mark.parametrize('name', SPLIT_CASES)
-def test_split_update_matches_unsplit_update(product, name, monkeypatch):
-    """The split SHPF half-step (G_y in the z-line kernel, G_x/G_z in the y-line kernel,
-    shpf_split.cuh, default) and the z-line derivative + full y-line update pair compute
-    bit-identical fields: every component sees the same expression and operands."""
+@pytest.mark.parametrize('name', [k['name'] for k in C.DIGEST_CASES])
+def test_large_case_vs_oracle_and_reference_digest(product, name):
+    """The benchmarked kernel instantiations (256-point lines: k_zline<.,256,16> /
+    k_yline_update<.,256,.> with the shared twiddle table; 512-point three-stage plans) and the
+    BASELINE-config shapes: full fields against the oracle live, sub-sample / norms / probe signal
+    against the digest of the real reference's run."""
     case = C.CASES_BY_NAME[name]
-    monkeypatch.setenv('IES_B200_SPLIT', '1')
+    got = H.run_product(product, case)
+    tol = H.tolerance(case)
+    derr = C.digest_errors(got, H.load_digest(case))
+    assert max(derr.values()) <= tol, (name, 'digest', derr)
+    want = C.run_oracle(case)
+    errs = H.worst_rel_l2(got, want)
+    assert max(errs.values()) <= tol, (name, 'oracle', errs)
+    if 'probe' in want:
+        assert C.rel_l2(got['probe'], want['probe']) <= tol
+
+
+FUSED_CASES = ['shpf_f64_xpml_64', 'shpf_f64_allpml_64_r2', 'shpf_f32_allpml_64', 'shpf_f64_xpml_256',
+               'shpf_f64_allpml_256_r2', 'shpf_f32_xpml_256', 'cfg3_shpf_32x256x256', 'cfg5_shpf_24x512x512_sphere']
+
+
+@pytest.mark.parametrize('name', FUSED_CASES)
+@pytest.mark.parametrize('ring', [0, 6])
+def test_fused_half_step_matches_two_kernel_path(product, name, ring, monkeypatch):
+    """The single-launch SHPF half-step (shpf_fused.cuh: z-line and y-line tiles as two roles of one
+    grid, scratch ring in L2) computes bit-identical fields to k_zline + k_yline_update: every
+    component sees the same expression and operands.  ring = 0: full-size scratch; 6: a ring of six
+    planes with a lead of two, so slots are reused many times within a launch."""
+    case = C.CASES_BY_NAME[name]
+    monkeypatch.setenv('IES_B200_FUSED', '1')
+    monkeypatch.setenv('IES_B200_FUSED_RING', str(ring))
+    monkeypatch.setenv('IES_B200_FUSED_LEAD', '2')
     a = H.run_product(product, case)
-    monkeypatch.setenv('IES_B200_SPLIT', '0')
+    monkeypatch.setenv('IES_B200_FUSED', '0')
     b = H.run_product(product, case)
     for n in C.FIELDS:
         assert np.array_equal(np.asarray(a[n]), np.asarray(b[n])), n
+
+
+def test_shpf_x_bloch_with_yz_bloch_is_refused(product):
+    """The reference evaluates the y/z Bloch terms after the x ghost copies (space.py:1898-1930); the
+    fused multiplier cannot, so the combination raises instead of returning different fields."""
+    case = dict(C.CASES_BY_NAME['shpf_c128_bloch_x'])
+    case['bbc'] = {'x': True, 'y': True, 'z': False}
+    with pytest.raises(NotImplementedError):
+        H.run_product(product, case)
 
 
 def _run_with_env(product, case, monkeypatch, **env):

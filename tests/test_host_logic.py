@@ -103,7 +103,7 @@ def test_full_multiplier_is_hermitian_extension():
     k = np.fft.rfftfreq(n, d) * 2 * np.pi
     ik = (1j * k).astype(np.complex128)
     shift = np.exp(ik * d / 2)
-    self = types.SimpleNamespace(field_dtype=np.float64)
+    self = types.SimpleNamespace(field_dtype=np.float64, mmtdtype=np.complex128)
     full = Basic3D._full_multiplier(self, ik, shift, 0., n)
     rng = np.random.default_rng(0)
     a, b = rng.standard_normal(n), rng.standard_normal(n)

@@ -22,13 +22,20 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 
 VARIANTS = [
-    ('base', dict()),                                   # engine defaults
-    ('noctile', dict(ctile=0)),
-    ('split', dict(split=1)),
-    ('palette', dict(palette=1, ctile=0)),
+    ('base', dict(fused=0)),                            # two-kernel path (k_zline + k_yline_update)
+    ('fused_full_l3', dict(fused=1, fused_ring=0, fused_lead=3)),     # single launch, full-size scratch
+    ('fused_full_l1', dict(fused=1, fused_ring=0, fused_lead=1)),
+    ('fused_full_l8', dict(fused=1, fused_ring=0, fused_lead=8)),
+    ('fused_r16_l3', dict(fused=1, fused_ring=16, fused_lead=3)),     # scratch ring of 16 planes (16 MiB)
+    ('fused_r32_l3', dict(fused=1, fused_ring=32, fused_lead=3)),
+    ('fused_r32_l8', dict(fused=1, fused_ring=32, fused_lead=8)),
+    ('fused_r64_l3', dict(fused=1, fused_ring=64, fused_lead=3)),
+    ('fused_r8_l2', dict(fused=1, fused_ring=8, fused_lead=2)),
+    ('noctile', dict(fused=0, ctile=0)),
+    ('palette', dict(fused=0, palette=1, ctile=0)),
 ]
-ALL_OPTS = ('split', 'palette', 'ctile')
-DEFAULTS = dict(split=0, palette=0, ctile=1)
+ALL_OPTS = ('fused', 'fused_ring', 'fused_lead', 'palette', 'ctile')
+DEFAULTS = dict(fused=0, fused_ring=0, fused_lead=3, palette=0, ctile=1)
 
 
 def main():
