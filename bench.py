@@ -1,21 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- headline benchmark of the b200 engine (BASELINE.json):
-Mcell-updates/s of fp64 SHPF on 1024x256x256 per GPU, CPML in x, plane-wave
-Gaussian source, two eps_r=4 slabs with an air cylinder through each
-(examples/reflectance_transmittance/RT_hole_slabs_short_input_src.py geometry).
-
-One step = Setter.put_src + Basic3D.updateH + Basic3D.updateE of ONE space through
-the product's public Python API (ctypes -> C-ABI -> sm_100a kernels).
+"""bench.py -- benchmark of the b200 engine on the workloads BASELINE.json names.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--config headline|strong|mie]
 
-N > 1 is launched by torchrun (one rank per GPU); each rank owns an x-slab of
-1024x256x256 cells (weak scaling, global Nx = 1024*N) and exchanges one yz-plane
-per half-step with its neighbours over NCCL.  `--impl reference` times the CPU
-restatement of the reference's algorithm (oracle/, the reference itself is pure
-Python and cannot travel to the GPU box) on the host cores.
+  headline (default, the metric's workload): fp64 SHPF, 1024x256x256 cells PER GPU (weak scaling,
+           global Nx = 1024 N), CPML in x, periodic y/z, plane-wave Gaussian source, two eps_r=4 slabs
+           with an air cylinder through each (examples/reflectance_transmittance/
+           RT_hole_slabs_short_input_src.py geometry) -- BASELINE config 3.
+  strong : the same 1024x256x256 grid split into N x-slabs (config 3's "x-slab split over 2/4/8").
+  mie    : fp64 SHPF, 256x512x512 cells per GPU (2048x512x512 at N = 8), CPML on all six faces,
+           eps_r = 4 sphere, plane-wave source (examples/mie/mie_scattering.py) -- BASELINE config 5.
+
+One step = Setter.put_src + Basic3D.updateH + Basic3D.updateE of ONE space through the product's
+public Python API (ctypes -> C-ABI -> sm_100a kernels).  N > 1: one rank per GPU (launched by
+`python -m torch.distributed.run`), x-slabs exchange one yz-plane per half-step over CUDA IPC /
+NVLink inside libies_b200.so (comm.IpcComm); torch.distributed (NCCL) is used by THIS script only
+for the contract's barrier and max-over-ranks reduction of the timings.
+
+Before anything is timed the same kernel instantiations run a short sub-problem (N ranks when
+N > 1) and are compared with the oracle: `parity_check` in the JSON line.
+
+`--impl reference` times the reference's own NumPy implementation on the host cores: the real
+reference modules when oracle/_ref/ travelled to this box (cpu_baseline.kind "reference"), else
+the oracle port.
 """
 import argparse
+import contextlib
 import ctypes as C
 import json
 import os
@@ -30,37 +41,69 @@ sys.path.insert(0, ROOT)
 
 um = 1e-6
 C0 = 299792458.0
-NY = NZ = 256
-NX_PER_GPU = 1024
 BYTES_PER_CELL_UPDATE = 160.0      # fp64 real fields, both half-steps
-METRIC = "Mcell-updates/s (fp64 SHPF 1024x256x256 per GPU, CPML-x, plane-wave source)"
+FIELDS = ('Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz')
+
+WORKLOADS = {
+    'headline': dict(
+        metric="Mcell-updates/s (fp64 SHPF 1024x256x256 per GPU, CPML-x, plane-wave source)",
+        per_gpu=(1024, 256, 256), scaling='weak', gap=(720 * um / 1024, 512 * um / 256, 512 * um / 256),
+        pml={'x': '+-', 'y': '', 'z': ''}, npml=10, pbc={'x': False, 'y': True, 'z': True}, shape='slabs',
+        text="CPML x+- (npml 10), periodic y/z, 2 eps_r=4 slabs with air cylinder, Gaussian plane source Ey (soft)"),
+    'strong': dict(
+        metric="Mcell-updates/s (fp64 SHPF 1024x256x256 split into N x-slabs, CPML-x, plane-wave source)",
+        total=(1024, 256, 256), scaling='strong', gap=(720 * um / 1024, 512 * um / 256, 512 * um / 256),
+        pml={'x': '+-', 'y': '', 'z': ''}, npml=10, pbc={'x': False, 'y': True, 'z': True}, shape='slabs',
+        text="CPML x+- (npml 10), periodic y/z, 2 eps_r=4 slabs with air cylinder, Gaussian plane source Ey (soft)"),
+    'mie': dict(
+        metric="Mcell-updates/s (fp64 SHPF 256x512x512 per GPU, CPML on all faces, eps_r=4 sphere)",
+        per_gpu=(256, 512, 512), scaling='weak', gap=(1 * um, 1 * um, 1 * um),
+        pml={'x': '+-', 'y': '+-', 'z': '+-'}, npml=10, pbc={'x': False, 'y': False, 'z': False}, shape='sphere',
+        text="CPML on all six faces (npml 10), eps_r=4 sphere of radius 60 cells at the centre, Gaussian plane "
+             "source Ey (soft) -- examples/mie/mie_scattering.py"),
+}
 
 
-def geometry(nx_global):
-    dx, dy, dz = 720 * um / NX_PER_GPU, 512 * um / NY, 512 * um / NZ
-    dt = 0.25 * min(dx, dy, dz) / C0
-    return (dx, dy, dz), dt
+def grid_of(wl, world):
+    if 'per_gpu' in wl:
+        nx, ny, nz = wl['per_gpu']
+        return (nx * world, ny, nz)
+    return wl['total']
 
 
-def build_space(ns, nx_global, tsteps, comm=None, device=None, method='SHPF'):
-    """Space + source + structures of the headline workload through the public API."""
-    gap, dt = geometry(nx_global)
-    kw = dict(method=method, engine='b200')
+def build_space(ns, wl, world, tsteps, comm=None, device=None, engine='b200', grid=None):
+    """Space + source + structures of a workload through the reference-style public API."""
+    grid = grid or grid_of(wl, world)
+    gap = wl['gap']
+    dt = 0.25 * min(gap) / C0
+    kw = dict(method='SHPF', engine=engine)
     if comm is not None: kw['comm'] = comm
     if device is not None: kw['device'] = device
-    sp = ns.space.Basic3D((nx_global, NY, NZ), gap, dt, tsteps, np.float64, np.complex128, **kw)
+    sp = ns.space.Basic3D(grid, gap, dt, tsteps, np.float64, np.complex128, **kw)
     sp.malloc()
-    sp.apply_PML({'x': '+-', 'y': '', 'z': ''}, 10)
+    sp.apply_PML(wl['pml'], wl['npml'])
     sp.apply_BBC({'x': False, 'y': False, 'z': False})
-    sp.apply_PBC({'x': False, 'y': True, 'z': True})
-    Ly, Lz = 512 * um, 512 * um
-    xs = 0.2 * 720 * um
+    sp.apply_PBC(wl['pbc'])
+    Lx, Ly, Lz = grid[0] * gap[0], grid[1] * gap[1], grid[2] * gap[2]
+    xs = 0.2 * Lx
     setter = ns.source.Setter(sp, (xs, 0, 0), (xs, Ly, Lz), (0, 0, 0))
-    for (a, b) in ((160 * um, 260 * um), (460 * um, 560 * um)):
-        ns.structure.Box('slab', sp, (a, 0, 0), (b, Ly, Lz), 4., 1.)
-        ns.structure.Cylinder3D('hole', sp, 'x', 128 * um, (a, b), (Ly / 2, Lz / 2), 1., 1.)
+    if wl['shape'] == 'slabs':
+        for (a, b) in ((160. / 720 * Lx, 260. / 720 * Lx), (460. / 720 * Lx, 560. / 720 * Lx)):
+            ns.structure.Box('slab', sp, (a, 0, 0), (b, Ly, Lz), 4., 1.)
+            ns.structure.Cylinder3D('hole', sp, 'x', 0.25 * Ly, (a, b), (Ly / 2, Lz / 2), 1., 1.)
+    else:
+        rad = min(60, grid[0] // 2 - wl['npml'] - 2) * gap[0]
+        ns.structure.Sphere('diel_sphere', sp, (int(grid[0] / 2) - 1, int(grid[1] / 2) - 1, int(grid[2] / 2) - 1),
+                            rad, 4., 1.)
     src = ns.source.Gaussian(dt, 100 * um, 0.08, 2000, dtype=np.float64)
     return sp, setter, src
+
+
+def product_ns():
+    import types
+    import ies_b200
+    return types.SimpleNamespace(space=ies_b200.space, source=ies_b200.source,
+                                 structure=ies_b200.structure, collector=ies_b200.collector)
 
 
 def pinned_like(shape, dtype):
@@ -121,115 +164,204 @@ def measured_peak():
     return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s; MEASURED_PEAKS.json absent)'
 
 
-def ncu_traffic(kernel='k_yline_update'):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
+def ncu_traffic(kernel, config):
+    """DRAM bytes per launch of a kernel from the committed ncu capture
     (profiles/ncu_summary.json, written by tools/ncu_summary.py), or None."""
     p = os.path.join(ROOT, 'profiles', 'ncu_summary.json')
     try:
-        return json.load(open(p)).get(kernel, {}).get('dram_bytes_per_launch')
+        j = json.load(open(p))
+        key = kernel if config != 'mie' else kernel + '_mie'
+        return j.get(key, {}).get('dram_bytes_per_launch')
     except Exception:
         return None
 
 
+# ------------------------------------------------------------------ parity
+def parity_case(config, world):
+    """The sub-problem checked against the oracle before the timed region: the SAME kernel
+    instantiations (line lengths, dtype, CPML faces, fused single-launch path) on a few planes per rank."""
+    from oracle import cases as OC
+    if config == 'mie':
+        return OC._case('bench_parity_mie', 'SHPF', 'float64', (12 * world, 512, 512), steps=3, npml=10,
+                        pml=OC.ALLPML, src='plane', boxes=False, sphere=True, ranks=world)
+    return OC._case('bench_parity', 'SHPF', 'float64', (16 * world, 256, 256), steps=6, npml=4,
+                    pbc=OC.PBC_YZ, bbc=OC.NO, ranks=world)
+
+
+def parity_check(ns, config, rank, world, comm):
+    from oracle import cases as OC
+    case = parity_case(config, world)
+    mine = dict(case); mine['ranks'] = 1               # build_api builds THIS rank's slab; size comes from the comm
+    with contextlib.redirect_stdout(sys.stderr):
+        sp, setter = OC.build_api(ns, mine, 'b200')
+        for t in range(case['steps']):
+            OC.step_api(sp, setter, mine, t)
+        local = {n: np.asarray(getattr(sp, n)) for n in FIELDS}
+    if world > 1:
+        parts = {n: comm.gather(local[n], root=0) for n in FIELDS}
+    else:
+        parts = {n: [local[n]] for n in FIELDS}
+    out = None
+    if rank == 0:
+        got = {n: np.concatenate(parts[n], axis=0) for n in FIELDS}
+        want = OC.run_oracle(case)
+        errs = OC.group_rel_l2(got, want)
+        out = {"rel_l2_vs_oracle": max(errs.values()), "tolerance": 1e-10, "grid": list(case['grid']),
+               "steps": case['steps'], "ranks": world,
+               "transport": "CUDA IPC halo (comm.IpcComm)" if world > 1 else "single slab",
+               "what": "fields after the sub-run through the same API / kernels as the timed region, "
+                       "compared with oracle/ies_oracle.py (N-rank OracleCluster when N > 1)"}
+        assert out["rel_l2_vs_oracle"] <= 1e-10, out
+    del sp
+    return out
+
+
 # ------------------------------------------------------------------ CPU baseline
-def oracle_sample_rate(nx_s, steps, warmup, seed=0):
-    """Oracle (NumPy restatement of the reference) on an nx_s x 256 x 256 x-slab sample of
-    the headline workload; returns (Mcell-updates/s, seconds per step)."""
-    from oracle import ies_oracle as O
-    gap, dt = geometry(nx_s)
-    sp = O.OracleSpace((nx_s, NY, NZ), gap, dt, steps + warmup + 1, np.float64, np.complex128, method='SHPF')
-    sp.apply_PML({'x': '+-', 'y': '', 'z': ''}, 10)
-    sp.apply_PBC({'x': False, 'y': True, 'z': True})
-    setter = O.OracleSetter(sp, (0.2 * nx_s * gap[0], 0, 0), (0.2 * nx_s * gap[0], 512 * um, 512 * um), (0, 0, 0))
-    sp.eps[nx_s // 4: nx_s // 2] *= 4.
-    sp.init_update_constants()
-    rng = np.random.default_rng(seed)
-    for n in ('Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz'):
-        getattr(sp, n)[...] = rng.uniform(-1, 1, sp.loc_grid)
+def reference_available():
+    from oracle import ref_shims
+    return ref_shims.reference_available()
+
+
+def cpu_sample_rate(config, nx_s, steps, warmup, seed=0, use_reference=True):
+    """The reference's own updateH/updateE (real modules under oracle/ref_shims.py when present, else
+    the oracle port) on an nx_s-plane x-slab sample of the workload; returns (Mcell-updates/s, s/step)."""
+    wl = WORKLOADS[config]
+    grid = (nx_s,) + tuple(grid_of(wl, 1)[1:])
+    if use_reference and reference_available():
+        from oracle import ref_shims
+        ns = ref_shims.load_reference()
+        with contextlib.redirect_stdout(sys.stderr):
+            sp, setter, src = build_space(ns, wl, 1, steps + warmup + 1, engine='cupy', grid=grid)
+            sp.init_update_constants()
+        rng = np.random.default_rng(seed)
+        for n in FIELDS:
+            getattr(sp, n)[...] = rng.uniform(-1, 1, sp.Ex.shape)
+
+        def step(t):
+            setter.put_src('Ey', src.pulse_re(t), 'soft')
+            sp.updateH(t); sp.updateE(t)
+    else:
+        from oracle import ies_oracle as O
+        gap = wl['gap']
+        dt = 0.25 * min(gap) / C0
+        sp = O.OracleSpace(grid, gap, dt, steps + warmup + 1, np.float64, np.complex128, method='SHPF')
+        sp.apply_PML(wl['pml'], wl['npml'])
+        sp.apply_PBC(wl['pbc'])
+        setter = O.OracleSetter(sp, (0.2 * nx_s * gap[0], 0, 0),
+                                (0.2 * nx_s * gap[0], grid[1] * gap[1], grid[2] * gap[2]), (0, 0, 0))
+        sp.eps[nx_s // 4: nx_s // 2] *= 4.
+        sp.init_update_constants()
+        rng = np.random.default_rng(seed)
+        for n in FIELDS:
+            getattr(sp, n)[...] = rng.uniform(-1, 1, sp.loc_grid)
+
+        def step(t):
+            setter.put_src('Ey', O.gaussian_pulse_re(t, dt, 100 * um, 0.08, 2000), 'soft')
+            sp.update_h(t); sp.update_e(t)
     t = 0
     for _ in range(warmup):
-        setter.put_src('Ey', O.gaussian_pulse_re(t, dt, 100 * um, 0.08, 2000), 'soft')
-        sp.update_h(t); sp.update_e(t); t += 1
+        step(t); t += 1
     t0 = time.perf_counter()
     for _ in range(steps):
-        setter.put_src('Ey', O.gaussian_pulse_re(t, dt, 100 * um, 0.08, 2000), 'soft')
-        sp.update_h(t); sp.update_e(t); t += 1
+        step(t); t += 1
     el = time.perf_counter() - t0
-    return nx_s * NY * NZ * steps / el / 1e6, el / steps
+    return grid[0] * grid[1] * grid[2] * steps / el / 1e6, el / steps
 
 
-def _ref_worker(args):
-    nx_s, steps, warmup, seed = args
+def _ref_worker(a):
+    config, nx_s, steps, warmup, seed = a
     os.environ['OMP_NUM_THREADS'] = '1'
-    return oracle_sample_rate(nx_s, steps, warmup, seed)
+    return cpu_sample_rate(config, nx_s, steps, warmup, seed)
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     import multiprocessing as mp
+    wl = WORKLOADS[args.config]
     try:
         cores = len(os.sched_getaffinity(0))
     except AttributeError:
         cores = os.cpu_count() or 1
     R = max(1, min(cores, 64, int(os.environ.get('IES_BENCH_REF_MAX_RANKS', 64))))
-    nx_s = 16
+    ny, nz = grid_of(wl, 1)[1:]
+    nx_s = 24 if args.config == 'mie' else 16       # all-face CPML needs >= 2 npml + 2 planes
     # keep the whole run within a few minutes: ~0.35 s per rank-step at 16x256x256
-    steps = max(1, min(args.steps, 60))
+    steps = max(1, min(args.steps, 60 if args.config != 'mie' else 8))
     warm = max(1, min(args.warmup, 3))
+    kind = "reference" if reference_available() else "port"
     ctx = mp.get_context('fork')
     t0 = time.perf_counter()
     with ctx.Pool(R) as pool:
-        res = pool.map(_ref_worker, [(nx_s, steps, warm, s) for s in range(R)])
+        res = pool.map(_ref_worker, [(args.config, nx_s, steps, warm, s) for s in range(R)])
     wall = time.perf_counter() - t0
     agg = float(sum(r[0] for r in res))
     spp = float(max(r[1] for r in res))
-    sample = (f"{R} independent x-slab ranks of {nx_s}x{NY}x{NZ} cells (one per usable host core), "
-              f"{steps} timed + {warm} warm-up steps each, NumPy/pocketfft single-threaded per rank; "
-              f"halo exchange omitted (2 planes per half-step, <0.1% of rank time); wall {wall:.1f} s")
+    what = ("the UNMODIFIED reference modules (oracle/_ref/ copy of space.py, source.py, structure.py under "
+            "oracle/ref_shims.py: cupy->NumPy alias, engine='cupy' branch)" if kind == "reference"
+            else "the oracle port of the reference's updateH/updateE (oracle/_ref/ is not on this box)")
+    sample = (f"{what}; {R} independent x-slab ranks of {nx_s}x{ny}x{nz} cells (one per usable host core), "
+              f"{steps} timed + {warm} warm-up steps each, NumPy/pocketfft single-threaded per rank; halo "
+              f"exchange omitted (2 planes per half-step, <0.1% of rank time); wall {wall:.1f} s")
     line = {
-        "impl": "reference", "metric": METRIC, "value": agg, "unit": "Mcell-updates/s",
+        "impl": "reference", "metric": wl['metric'], "value": agg, "unit": "Mcell-updates/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": spp * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": wl['scaling'], "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "SHPF fp64 1024x256x256-shaped x-slab samples on host cores (oracle port of the "
-                               "reference's updateH/updateE; the reference is pure Python and is not on this box)",
+        "config": {"workload": f"SHPF fp64 {args.config}: {nx_s}x{ny}x{nz}-cell x-slab samples of the workload on "
+                               f"host cores; {wl['text']}",
                    "steps_requested": args.steps},
-        "cpu_baseline": {"value": agg, "unit": "Mcell-updates/s", "cores": R, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": agg, "unit": "Mcell-updates/s", "cores": R, "kind": kind, "sample": sample},
         "e2e": {"value": agg, "unit": "Mcell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    # one full-size single-rank measurement beside the slab samples (the reference keeps ~34 full arrays:
+    # ~17 GiB at 1024x256x256), when the host has the memory and the caller allows the minute it takes
+    if args.config == 'headline' and os.environ.get('IES_BENCH_REF_FULL', '1') != '0':
+        try:
+            import psutil
+            if psutil.virtual_memory().available > 48 * 2 ** 30:
+                v, s = cpu_sample_rate('headline', 1024, 1, 1, 0)
+                line["cpu_baseline"]["full_size_single_rank"] = {
+                    "value": v, "unit": "Mcell-updates/s", "cores": 1, "seconds_per_step": s,
+                    "sample": "one rank, the whole 1024x256x256 grid, 1 warm-up + 1 timed step"}
+        except Exception as e:                       # never lose the line over the optional extra
+            line["cpu_baseline"]["full_size_single_rank"] = {"error": str(e)}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------ GPU arm
 def run_b200(args, rank, world, local_rank):
-    import types
     import torch
-    import ies_b200
     from ies_b200 import _lib, comm as icomm
-    ns = types.SimpleNamespace(space=ies_b200.space, source=ies_b200.source,
-                               structure=ies_b200.structure, collector=ies_b200.collector)
+    ns = product_ns()
     lib = _lib.load()
+    wl = WORKLOADS[args.config]
     dist = None
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-        comm = icomm.TorchComm()
-    else:
-        comm = icomm.SingleComm()
+    os.environ.setdefault('IES_B200_DEVICE', str(local_rank))
+    comm = icomm.default_comm()                          # IpcComm under a multi-rank launch, else SingleComm
     K, W = args.steps, args.warmup
-    nx_global = NX_PER_GPU * world
-    import contextlib
+    grid = grid_of(wl, world)
+
+    # ---------------- parity of the benchmarked instantiation, before anything is timed ----------------
+    par = None
+    if not args.no_parity:
+        par = parity_check(ns, args.config, rank, world, comm)
+
     with contextlib.redirect_stdout(sys.stderr):      # the API mirrors the reference's set-up prints
-        sp, setter, src = build_space(ns, nx_global, K + W + 8, comm=comm, device=local_rank)
-    ncell_local = sp.myNx * NY * NZ
+        sp, setter, src = build_space(ns, wl, world, K + W + 8, comm=comm, device=local_rank)
+    ny, nz = grid[1], grid[2]
+    ncell_local = sp.myNx * ny * nz
+    ncell_total = grid[0] * ny * nz
 
     # host inputs (pinned): random fields (SURVEY 8d) and the two coefficient arrays
     rng = np.random.default_rng(1234 + rank)
     host = {}
     keep = []
-    for n in ('Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz'):
+    for n in FIELDS:
         a, t = pinned_like(sp.loc_grid, np.float64)
         a[...] = rng.uniform(-1, 1, sp.loc_grid)
         host[n] = a; keep.append(t)
@@ -256,6 +388,8 @@ def run_b200(args, rank, world, local_rank):
         sp.updateE(t)
 
     def barrier():
+        sp.sync()
+        torch.cuda.synchronize()
         if dist is not None: dist.barrier()
         sp.sync()
         torch.cuda.synchronize()
@@ -265,10 +399,6 @@ def run_b200(args, rank, world, local_rank):
         t = torch.tensor([x], dtype=torch.float64, device='cuda')
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
-
-    if world > 1:
-        # engine and NCCL share comm's dedicated stream from the first step on
-        sp._use_stream(comm._stream_for(local_rank).cuda_stream)
 
     # ---------------- device-resident throughput (value) ----------------
     upload_all()
@@ -289,14 +419,14 @@ def run_b200(args, rank, world, local_rank):
     launches = lib.ies_launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
     prof = {}
-    for slot, nm in ((0, 'k_zline'), (1, 'k_yline_update')):
+    for slot, nm in ((0, 'z'), (1, 'y')):
         tot, cnt = C.c_double(), C.c_int64()
         _lib.check(lib.ies_profile_read(sp._ctx, slot, C.byref(tot), C.byref(cnt)))
         prof[nm] = (tot.value, cnt.value)
     _lib.check(lib.ies_profile(sp._ctx, 0))
     ms_total = max_over_ranks(ms.value)
     ms_step = ms_total / K
-    value = ncell_local * world * K / (ms_total * 1e-3) / 1e6
+    value = ncell_total * K / (ms_total * 1e-3) / 1e6
 
     # sanity: the fields are still finite after the timed steps
     probe = np.asarray(sp.Ey[sp.myNx // 2, :4, :4])
@@ -314,7 +444,7 @@ def run_b200(args, rank, world, local_rank):
     for _ in range(Ke):
         step(te); te += 1
     d2h = 0
-    for n in ('Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz'):
+    for n in FIELDS:
         _lib.check(lib.ies_get_field(sp._ctx, _lib.COMP[n], _lib.I3(0, 0, 0), _lib.I3(*sp.loc_grid),
                                      out_host.ctypes.data_as(C.c_void_p)))
         d2h += out_host.nbytes
@@ -324,59 +454,68 @@ def run_b200(args, rank, world, local_rank):
     wall_e2e = (time.perf_counter() - t0) * 1e3
     e2e_ms = max_over_ranks(max(ms2.value, wall_e2e))
     h2d = 8 * ncell_local * 8
-    e2e_val = ncell_local * world * Ke / (e2e_ms * 1e-3) / 1e6
+    e2e_val = ncell_total * Ke / (e2e_ms * 1e-3) / 1e6
 
     if rank != 0:
         if dist is not None: dist.destroy_process_group()
         return
 
     peak, peak_src = measured_peak()
-    ky_ms, ky_n = prof['k_yline_update']
-    kz_ms, kz_n = prof['k_zline']
+    ky_ms, ky_n = prof['y']
+    kz_ms, kz_n = prof['z']
     ky_avg = ky_ms / max(ky_n, 1)
     kz_avg = kz_ms / max(kz_n, 1)
+    fused = kz_n == 0
     # Algorithmic bytes of one half-step of the slab: 80 B per cell = read 6 fields +
-    # 1 coefficient array, write 3 fields.  The half-step is two launches (k_zline derivative
-    # pass + k_yline_update); the dominant kernel k_yline_update carries all of these bytes
-    # (k_zline only produces scratch), so achieved = 80 B x cells / its launch duration.
+    # 1 coefficient array, write 3 fields.  Fused path: ONE launch (k_shpf_fused) per half-step carries
+    # them.  Two-kernel path: the dominant kernel k_yline_update carries them (k_zline only produces scratch).
     alg_bytes_launch = 0.5 * BYTES_PER_CELL_UPDATE * ncell_local
     achieved = alg_bytes_launch / (ky_avg * 1e-3) / 1e9 if ky_avg > 0 else 0.0
     step_gbs = BYTES_PER_CELL_UPDATE * ncell_local / (ms_step * 1e-3) / 1e9
-    traffic = ncu_traffic('k_yline_update')
+    kname = 'k_shpf_fused' if fused else 'k_yline_update'
+    traffic = ncu_traffic(kname, args.config)
     roofline = {
-        "bound": "hbm", "kernel": "k_yline_update<double,false,256> (y-line FFT derivative + fused update/CPML)",
+        "bound": "hbm",
+        "kernel": (f"k_shpf_fused<double,{ny},{nz}> (one launch per half-step: z-line FFT tiles + y-line FFT / update / "
+                   "CPML tiles as two roles of one grid)" if fused else
+                   f"k_yline_update<double,false,{ny}> (y-line FFT derivative + fused update/CPML)"),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": traffic, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes_launch,
         "avg_launch_ms": ky_avg, "launches_timed": ky_n,
         "kernel_share_of_step": (ky_ms / K) / ms_step if ms_step > 0 else None,
         "dram_gbs_from_ncu_traffic": (traffic / (ky_avg * 1e-3) / 1e9) if (traffic and ky_avg > 0) else None,
-        "zline": {"kernel": "k_zline<double,false,256,16> (z-line FFT derivative pass -> scratch)",
-                  "avg_launch_ms": kz_avg, "launches_timed": kz_n,
-                  "share_of_step": (kz_ms / K) / ms_step if ms_step > 0 else None,
-                  "traffic": ncu_traffic('k_zline')},
-        "step": {"achieved": step_gbs, "frac": step_gbs / peak,
-                 "note": "whole leap-frog step (both kernels, both half-steps, source injection) at 160 B per "
-                         "cell-update: the figure comparable with the 60 % target"},
+        "step_achieved": step_gbs, "step_frac": step_gbs / peak,
+        "step_note": "whole leap-frog step (both half-steps, source injection, halo) at 160 B per cell-update on "
+                     "this rank's slab: the figure comparable with the 60 % target",
     }
+    if not fused:
+        roofline["zline"] = {"kernel": f"k_zline<double,false,{nz},16> (z-line FFT derivative pass -> scratch)",
+                             "avg_launch_ms": kz_avg, "launches_timed": kz_n,
+                             "share_of_step": (kz_ms / K) / ms_step if ms_step > 0 else None,
+                             "traffic": ncu_traffic('k_zline', args.config)}
 
     cpu = None
-    if world == 1:
-        nx_s = 64
-        v, spp = oracle_sample_rate(nx_s, 2, 1)
-        cpu = {"value": v, "unit": "Mcell-updates/s", "cores": 1, "kind": "port",
-               "sample": f"oracle (NumPy restatement of the reference's updateH/updateE) on a {nx_s}x{NY}x{NZ} "
-                         f"x-slab of the same workload, 1 warm-up + 2 timed steps, one core ({spp:.2f} s/step)"}
+    if world == 1 and not args.no_cpu:
+        nx_s = 64 if args.config != 'mie' else 24
+        v, spp = cpu_sample_rate(args.config, nx_s, 2, 1)
+        kind = "reference" if reference_available() else "port"
+        cpu = {"value": v, "unit": "Mcell-updates/s", "cores": 1, "kind": kind,
+               "sample": (("the unmodified reference (oracle/_ref/ under oracle/ref_shims.py)" if kind == "reference" else
+                           "oracle (NumPy restatement of the reference's updateH/updateE)") +
+                          f" on a {nx_s}x{ny}x{nz} x-slab of the same workload, 1 warm-up + 2 timed steps, "
+                          f"one core ({spp:.2f} s/step)")}
 
+    per = sp.loc_grid
     line = {
-        "metric": METRIC, "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "metric": wl['metric'], "value": value, "unit": "Mcell-updates/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": wl['scaling'],
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"SHPF fp64 {NX_PER_GPU}x{NY}x{NZ} cells per GPU (global {nx_global}x{NY}x{NZ}), "
-                               "CPML x+- (npml 10), periodic y/z, 2 eps_r=4 slabs with air cylinder, "
-                               "Gaussian plane source Ey (soft); fields pre-filled uniform(-1,1)",
-                   "parallelism": f"x-slab x{world}" if world > 1 else "single slab",
-                   "l2": "working set 4.8 GB per GPU >> 126 MB L2 (no flush needed)",
+        "config": {"workload": f"{args.config}: SHPF fp64 {per[0]}x{per[1]}x{per[2]} cells per GPU (global "
+                               f"{grid[0]}x{grid[1]}x{grid[2]}), {wl['text']}; fields pre-filled uniform(-1,1)",
+                   "parallelism": (f"x-slab x{world}, halo planes over CUDA IPC / NVLink (copy engine + "
+                                   "stream-ordered flags)") if world > 1 else "single slab",
+                   "l2": f"working set {8 * ncell_local * 8 / 1e9:.1f} GB per GPU >> 126 MB L2 (no flush needed)",
                    "timing": "CUDA events on the engine stream, max over ranks"},
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": "Mcell-updates/s", "h2d_bytes_per_step": h2d / Ke,
@@ -384,6 +523,7 @@ def run_b200(args, rank, world, local_rank):
                 "note": "H2D of 6 fields + 2 coefficient arrays (pinned), K steps, D2H of 6 fields, all timed"},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "parity_check": par,
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
@@ -397,6 +537,9 @@ def main():
     ap.add_argument('--steps', type=int, default=100)      # >= 20 warm-up + >= 100 timed steps
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--config', default='headline', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-parity', action='store_true', help='skip the oracle comparison before the timed region')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (N = 1)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get('RANK', 0))
@@ -406,10 +549,11 @@ def main():
         run_reference_arm(args, rank, world)
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
-        # convenience: re-launch under torchrun
+        # convenience: re-launch one rank per GPU
         cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={args.gpus}',
                '--master-addr', '127.0.0.1', '--master-port', '29531', os.path.abspath(__file__),
-               '--gpus', str(args.gpus), '--steps', str(args.steps), '--warmup', str(args.warmup)]
+               '--gpus', str(args.gpus), '--steps', str(args.steps), '--warmup', str(args.warmup),
+               '--config', args.config] + (['--no-parity'] if args.no_parity else [])
         sys.exit(subprocess.call(cmd))
     run_b200(args, rank, world, local_rank)
 

@@ -71,6 +71,10 @@ SIGNATURES = {
     'ies_halo_send_ptr': (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     'ies_halo_recv_ptr': (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(C.c_int64)]),
     'ies_halo_copy': (C.c_int, [_vp, _vp, C.c_int]),
+    'ies_halo_ipc_export': (C.c_int, [_vp, _vp]),
+    'ies_halo_ipc_connect': (C.c_int, [_vp, C.c_int, _vp]),
+    'ies_halo_push': (C.c_int, [_vp, C.c_int]),
+    'ies_halo_wait': (C.c_int, [_vp, C.c_int]),
     'ies_put_src': (C.c_int, [_vp, C.c_int, I3, I3, C.c_double, C.c_double, C.c_int, _vp, _vp, _vp]),
     'ies_get_field': (C.c_int, [_vp, C.c_int, I3, I3, _vp]),
     'ies_set_field': (C.c_int, [_vp, C.c_int, I3, I3, _vp]),
@@ -87,6 +91,7 @@ SIGNATURES = {
     'ies_timer_start': (C.c_int, [_vp]),
     'ies_timer_stop': (C.c_int, [_vp, C.POINTER(C.c_double)]),
     'ies_profile': (C.c_int, [_vp, C.c_int]),
+    'ies_fused_prof_read': (C.c_int, [_vp, C.POINTER(C.c_uint64)]),
     'ies_profile_read': (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
 }
 

@@ -8,10 +8,11 @@ view plus `exchange(space, half)`:
 * SingleComm  -- one slab, nothing to exchange.
 * LocalComm   -- several slabs driven by ONE process (same or different GPUs):
                  cudaMemcpyPeerAsync between contexts, event ordered (ies_halo_copy).
-* TorchComm   -- one process per GPU (torchrun): torch.distributed point-to-point
-                 (NCCL over NVLink for CUDA planes; gloo for the CPU tests).  The
-                 planes are the engine's own device buffers wrapped as tensors --
-                 torch is plumbing only.
+* IpcComm     -- one process per GPU (torchrun / any launcher setting RANK, WORLD_SIZE,
+                 LOCAL_RANK): CUDA IPC peer-mapped receive planes, copy-engine pushes over
+                 NVLink, stream-ordered flags (ies_halo_push / ies_halo_wait); the ranks
+                 find each other through SocketStore (standard library only -- no torch,
+                 no MPI in the package).
 """
 import os
 
@@ -75,123 +76,190 @@ class LocalComm:
         raise NotImplementedError("LocalComm.gather: use ies_b200.space.gather_local")
 
 
-class _DevPlane:
-    """__cuda_array_interface__ view of an engine-owned device buffer."""
+class SocketStore:
+    """Rendezvous for one-process-per-GPU runs on one node (the role `mpirun`'s wire-up plays
+    for the reference, README.md:131-135): rank 0 serves a tiny key/value + barrier protocol
+    over TCP on 127.0.0.1, the other ranks connect.  Pure standard library; values are bytes."""
 
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {
-            'shape': (nbytes,), 'typestr': '|u1', 'data': (int(ptr), False), 'version': 2, 'strides': None}
+    def __init__(self, rank, size, addr='127.0.0.1', port=None, timeout=300.):
+        import socket
+        import struct
+        import threading
+        self.rank, self.size, self.timeout = rank, size, timeout
+        self._struct = struct
+        if port is None:
+            port = int(os.environ.get('IES_B200_PORT', int(os.environ.get('MASTER_PORT', '29500')) + 1017))
+        self._server = None
+        if rank == 0:
+            self._kv, self._bar = {}, {}
+            self._cv = threading.Condition()
+            srv = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+            srv.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+            srv.bind((addr, port))
+            srv.listen(size + 4)
+            self._server = srv
+            threading.Thread(target=self._accept_loop, daemon=True).start()
+        import time
+        t0 = time.time()
+        while True:
+            try:
+                self._sock = socket.create_connection((addr, port), timeout=timeout)
+                break
+            except OSError:
+                if time.time() - t0 > timeout:
+                    raise
+                time.sleep(0.05)
+        self._sock.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+        self._gen = 0
+
+    # ---- wire format: 4-byte length + pickled tuple
+    def _send(self, sock, obj):
+        import pickle
+        b = pickle.dumps(obj, protocol=4)
+        sock.sendall(self._struct.pack('<I', len(b)) + b)
+
+    def _recv(self, sock):
+        import pickle
+
+        def rd(n):
+            buf = b''
+            while len(buf) < n:
+                c = sock.recv(n - len(buf))
+                if not c:
+                    raise ConnectionError('store connection closed')
+                buf += c
+            return buf
+        (n,) = self._struct.unpack('<I', rd(4))
+        return pickle.loads(rd(n))
+
+    def _accept_loop(self):
+        import threading
+        while True:
+            try:
+                conn, _ = self._server.accept()
+            except OSError:
+                return
+            threading.Thread(target=self._serve, args=(conn,), daemon=True).start()
+
+    def _serve(self, conn):
+        try:
+            while True:
+                msg = self._recv(conn)
+                op = msg[0]
+                if op == 'set':
+                    with self._cv:
+                        self._kv[msg[1]] = msg[2]
+                        self._cv.notify_all()
+                    self._send(conn, True)
+                elif op == 'get':
+                    with self._cv:
+                        ok = self._cv.wait_for(lambda: msg[1] in self._kv, timeout=self.timeout)
+                        val = self._kv.get(msg[1]) if ok else None
+                    self._send(conn, val)
+                elif op == 'del':
+                    with self._cv:
+                        for k in [k for k in self._kv if k.startswith(msg[1])]:
+                            del self._kv[k]
+                    self._send(conn, True)
+                elif op == 'barrier':
+                    with self._cv:
+                        self._bar[msg[1]] = self._bar.get(msg[1], 0) + 1
+                        self._cv.notify_all()
+                        ok = self._cv.wait_for(lambda: self._bar[msg[1]] >= self.size, timeout=self.timeout)
+                    self._send(conn, ok)
+        except (ConnectionError, OSError, EOFError):
+            return
+
+    def _call(self, *msg):
+        self._send(self._sock, msg)
+        return self._recv(self._sock)
+
+    def set(self, key, value): self._call('set', key, bytes(value))
+
+    def get(self, key):
+        v = self._call('get', key)
+        if v is None:
+            raise TimeoutError(f'store: key {key!r} never arrived')
+        return v
+
+    def delete_prefix(self, prefix): self._call('del', prefix)
+
+    def barrier(self):
+        self._gen += 1
+        if not self._call('barrier', self._gen):
+            raise TimeoutError('store: barrier timed out')
 
 
-class TorchComm:
-    """torch.distributed-backed neighbour exchange (one process per GPU)."""
+class IpcComm:
+    """One process per GPU on one node: the slabs' halo planes travel by copy engine into
+    peer-mapped (CUDA IPC) receive buffers, signalled by a stream-ordered flag write and
+    consumed behind a stream memory wait -- ies_halo_push / ies_halo_wait of the C-ABI.
+    Replaces the reference's blocking pickled mpi4py send/recv (space.py:645-670, 863-887);
+    rank/size/Barrier/gather keep the mpi4py spelling the scripts use."""
 
-    def __init__(self, group=None):
-        import torch.distributed as dist
-        self.dist = dist
-        self.group = group
-        self.rank = dist.get_rank(group)
-        self.size = dist.get_world_size(group)
-        self._views = {}
-        self._streams = {}
+    def __init__(self, rank=None, size=None, store=None):
+        self.rank = int(os.environ['RANK']) if rank is None else rank
+        self.size = int(os.environ['WORLD_SIZE']) if size is None else size
+        self.store = store if store is not None else SocketStore(self.rank, self.size)
+        self._nspaces = 0
 
     def Get_rank(self): return self.rank
     def Get_size(self): return self.size
-    def Barrier(self): self.dist.barrier(self.group)
-    def barrier(self): self.dist.barrier(self.group)
+    def Barrier(self): self.store.barrier()
+    def barrier(self): self.store.barrier()
 
-    # -- pattern shared with the gloo CPU tests ---------------------------------
-    def exchange_planes(self, half, send, recv):
-        """updateH (half 0): send my first planes to rank-1, receive rank+1's;
-        updateE (half 1): send my last planes to rank+1, receive rank-1's.
-        `send`/`recv` are lists of tensors (any device the backend supports)."""
-        dist = self.dist
-        dst = self.rank - 1 if half == 0 else self.rank + 1
-        src = self.rank + 1 if half == 0 else self.rank - 1
-        ops = []
-        if 0 <= dst < self.size:
-            ops += [dist.P2POp(dist.isend, t, dst, self.group) for t in send]
-        if 0 <= src < self.size:
-            ops += [dist.P2POp(dist.irecv, t, src, self.group) for t in recv]
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-
-    def _tensors(self, space):
+    def connect(self, space):
+        """Publish this slab's IPC handle, map the neighbours'.  Spaces are created in the same
+        order on every rank (SPMD script), so the k-th space of each rank forms one decomposition."""
         import ctypes as C
-        import torch
-        # cached on the space itself (an id()-keyed dict would hand a new space the views of a
-        # freed one that happened to get the same id)
-        if getattr(space, '_halo_views', None) is None:
-            lib = _lib.load()
-            dev = torch.device('cuda', space.device)
-            v = {}
-            for half in (0, 1):
-                for kind, fn in (('send', lib.ies_halo_send_ptr), ('recv', lib.ies_halo_recv_ptr)):
-                    ts = []
-                    for w in (0, 1):
-                        p, n = C.c_void_p(), C.c_int64()
-                        _lib.check(fn(space._ctx, half, w, C.byref(p), C.byref(n)))
-                        ts.append(torch.as_tensor(_DevPlane(p.value, n.value), device=dev))
-                    v[(half, kind)] = ts
-            space._halo_views = v
-        return space._halo_views
-
-    def _stream_for(self, device):
-        """One dedicated (non-default) torch stream per device, shared by NCCL and the engine.
-        torch's default stream cannot be used: its handle is 0, which the C-ABI
-        (ies_set_stream) reads as "use the context's own stream" -- the kernels would then
-        run unordered against the NCCL transfers."""
-        import torch
-        if device not in self._streams:
-            dev = device[0] if isinstance(device, tuple) else device
-            self._streams[device] = torch.cuda.Stream(device=dev)
-        return self._streams[device]
+        lib = _lib.load()
+        key = f'space{self._nspaces}'
+        self._nspaces += 1
+        h = (C.c_ubyte * 64)()
+        _lib.check(lib.ies_halo_ipc_export(space._ctx, h))
+        self.store.set(f'{key}/handle/{self.rank}', bytes(h))
+        for nbr, r in ((0, self.rank - 1), (1, self.rank + 1)):
+            if 0 <= r < self.size:
+                hb = (C.c_ubyte * 64).from_buffer_copy(self.store.get(f'{key}/handle/{r}'))
+                _lib.check(lib.ies_halo_ipc_connect(space._ctx, nbr, hb))
+        self.store.barrier()          # everybody mapped everybody before the first push
+        space._ipc_connected = True
 
     def exchange(self, space, half):
-        """In-order variant: transfer and kernels on one stream."""
-        import torch
-        v = self._tensors(space)
-        st = self._stream_for(space.device)
-        space._use_stream(st.cuda_stream)          # engine kernels and NCCL on the same stream
-        with torch.cuda.stream(st):
-            self.exchange_planes(half, v[(half, 'send')], v[(half, 'recv')])
-
-    def exchange_begin(self, space, half):
-        """Overlapped variant: the NCCL send/recv runs on a second stream once the engine
-        stream has finished the previous update (event), and returns the event the
-        neighbour-dependent part of the half-step has to wait for."""
-        import torch
-        v = self._tensors(space)
-        se = self._stream_for(space.device)
-        sc = self._stream_for((space.device, 'comm'))
-        space._use_stream(se.cuda_stream)
-        ready = torch.cuda.Event()
-        ready.record(se)                           # fields of the previous half-step are final
-        sc.wait_event(ready)
-        with torch.cuda.stream(sc):
-            self.exchange_planes(half, v[(half, 'send')], v[(half, 'recv')])
-            done = torch.cuda.Event()
-            done.record(sc)
-        return done
-
-    def exchange_end(self, space, done):
-        self._stream_for(space.device).wait_event(done)
+        """space.py:645-670 / 863-887: push my planes to the neighbour that needs them, then put the
+        wait for the planes I need in front of the update."""
+        if not getattr(space, '_ipc_connected', False):
+            self.connect(space)
+        lib = _lib.load()
+        _lib.check(lib.ies_halo_push(space._ctx, half))
+        _lib.check(lib.ies_halo_wait(space._ctx, half))
 
     def gather(self, arr, root=0):
-        out = [None] * self.size if self.rank == root else None
-        self.dist.gather_object(arr, out, dst=root, group=self.group)
+        """mpi4py-style gather of picklable objects to `root` (plotter.Graphtool.gather)."""
+        import pickle
+        self._gat = getattr(self, '_gat', 0) + 1
+        pre = f'gather{self._gat}/'
+        self.store.set(pre + str(self.rank), pickle.dumps(arr, protocol=4))
+        out = None
+        if self.rank == root:
+            out = [pickle.loads(self.store.get(pre + str(r))) for r in range(self.size)]
+        self.store.barrier()
+        if self.rank == root:
+            self.store.delete_prefix(pre)
         return out
 
 
+_default = None
+
+
 def default_comm():
-    """TorchComm when torch.distributed is initialised (torchrun), else SingleComm."""
-    try:
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            return TorchComm()
-    except ImportError:
-        pass
+    """IpcComm when the process was started as one rank of several (RANK / WORLD_SIZE in the
+    environment: torchrun, or any launcher that sets them), else SingleComm."""
+    global _default
+    if int(os.environ.get('WORLD_SIZE', '1')) > 1 and 'RANK' in os.environ:
+        if _default is None:
+            _default = IpcComm()
+        return _default
     return SingleComm()
 
 

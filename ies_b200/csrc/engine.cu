@@ -614,13 +614,27 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     if (const char* e = getenv("IES_B200_PALETTE")) c->use_palette = atoi(e);
     for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
     // spectral scratch is allocated on first use
-    c->use_fused = 0; c->fused_lead = 3; c->fused_ring_planes = 0; c->fused_ring_alloc = 0;
-    c->fused_ring[0] = c->fused_ring[1] = nullptr; c->fused_sync = nullptr; c->twz_t = nullptr;
+    c->use_fused = 1; c->fused_lead = 3; c->fused_ring_planes = 0; c->fused_ring_alloc = 0;
+    c->fused_ring[0] = c->fused_ring[1] = nullptr; c->fused_sync = nullptr; c->twz_t = nullptr; c->fused_prof = nullptr; c->fused_prof_mem = nullptr;
     if (const char* e = getenv("IES_B200_FUSED")) c->use_fused = atoi(e);
     if (const char* e = getenv("IES_B200_FUSED_LEAD")) c->fused_lead = std::max(1, atoi(e));
     if (const char* e = getenv("IES_B200_FUSED_RING")) c->fused_ring_planes = atoi(e);
-    const size_t pbytes = (size_t)cfg->ny * cfg->nz * c->esize;
-    for (int h = 0; h < 2; ++h) for (int w = 0; w < 2; ++w) if (dev_alloc(c, &c->halo_recv[h][w], pbytes)) return 1;
+    {
+        // halo block: [H y | H z | E y | E z | flags], planes 256-byte aligned
+        const size_t pbytes = (((size_t)cfg->ny * cfg->nz * c->esize) + 255) / 256 * 256;
+        c->halo_block_bytes = 4 * pbytes + 256;
+        if (dev_alloc(c, &c->halo_block, c->halo_block_bytes)) return 1;
+        for (int h = 0; h < 2; ++h) {
+            for (int w = 0; w < 2; ++w) c->halo_recv[h][w] = (char*)c->halo_block + (size_t)(2 * h + w) * pbytes;
+            c->halo_flag[h] = (unsigned*)((char*)c->halo_block + 4 * pbytes) + 16 * h;
+            c->push_seq[h] = c->wait_seq[h] = 0;
+        }
+        for (int n = 0; n < 2; ++n) {
+            c->peer_block[n] = nullptr;
+            for (int h = 0; h < 2; ++h) { c->peer_flag[n][h] = nullptr; c->peer_recv[n][h][0] = c->peer_recv[n][h][1] = nullptr; }
+        }
+        c->seq_ring = nullptr; c->flag_write_mode = 0;
+    }
     for (int h = 0; h < 2; ++h) for (int a = 0; a < 3; ++a) c->mult[h][a] = nullptr;
     // master twiddles W_N[k] = exp(-2 pi i k / N) per axis, in FFT precision
     const int dims[3] = {cfg->nx, cfg->ny, cfg->nz};
@@ -684,6 +698,8 @@ int ies_destroy(ies_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (void* p : c->owned) cudaFree(p);
     if (c->stage) cudaFree(c->stage);
+    for (int n = 0; n < 2; ++n) if (c->peer_block[n]) cudaIpcCloseMemHandle(c->peer_block[n]);
+    if (c->seq_ring) cudaFreeHost(c->seq_ring);
     cudaEventDestroy(c->ev_halo);
     cudaStreamDestroy(c->own_stream);
     delete c;
@@ -702,6 +718,11 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     else if (n == "fused") c->use_fused = v;
     else if (n == "fused_lead") c->fused_lead = v < 1 ? 1 : v;
     else if (n == "fused_ring") c->fused_ring_planes = v;
+    else if (n == "fused_prof") {               // 1: start (zeroed) per-phase cycle counters, 0: stop
+        if (v && !c->fused_prof_mem) { void* q; if (dev_alloc(c, &q, 16 * 8)) return 1; c->fused_prof_mem = (unsigned long long*)q; }
+        if (v) IES_CUDA(cudaMemsetAsync(c->fused_prof_mem, 0, 16 * 8, c->stream));
+        c->fused_prof = v ? c->fused_prof_mem : nullptr;
+    }
     else if (n == "reset_psi") {               // zero the CPML auxiliary state (restart a run on new fields)
         for (int h = 0; h < 2; ++h)
             for (const PmlTermDev& t : c->terms[h])
@@ -754,6 +775,13 @@ int ies_profile_read(ies_ctx* c, int slot, double* ms_total, int64_t* launches) 
         tot += f;
     }
     *ms_total = tot; *launches = (int64_t)n;
+    return 0;
+}
+int ies_fused_prof_read(ies_ctx* c, uint64_t* out16) {
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    IES_CUDA(cudaStreamSynchronize(c->stream));
+    if (!c->fused_prof_mem) { for (int q = 0; q < 16; ++q) out16[q] = 0; return 0; }
+    IES_CUDA(cudaMemcpy(out16, c->fused_prof_mem, 16 * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 int ies_sync(ies_ctx* c) { IES_CUDA(cudaSetDevice(c->cfg.device)); IES_CUDA(cudaStreamSynchronize(c->stream)); return 0; }
@@ -905,6 +933,92 @@ int ies_halo_recv_ptr(ies_ctx* c, int half, int which, void** dev, int64_t* byte
     *bytes = (int64_t)c->cfg.ny * c->cfg.nz * c->esize;
     return 0;
 }
+// ---- inter-process halo over CUDA IPC (one process per GPU) -----------------------------------
+// The receive planes and two arrival flags of a context live in ONE allocation whose IPC handle
+// the neighbours map.  A push = copy-engine transfers of my two send planes into the neighbour's
+// receive planes followed, in stream order, by a 4-byte write of the push count to its flag; the
+// receiver puts a stream memory wait (cuStreamWaitValue32, >=) in front of the update that reads
+// the planes.  No kernel, no host synchronisation, no event hand-shake between the processes.
+typedef int (*wait32_fn)(cudaStream_t, unsigned long long, unsigned, unsigned);    // CUresult (CUstream, CUdeviceptr, cuuint32_t, flags)
+static wait32_fn drv_entry(const char* name) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return (wait32_fn)fn;
+}
+
+int ies_halo_ipc_export(ies_ctx* c, void* handle64) {
+    if (!c || !handle64) { set_error("null argument"); return 1; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    IES_CUDA(cudaStreamSynchronize(c->stream));
+    cudaIpcMemHandle_t h;
+    IES_CUDA(cudaIpcGetMemHandle(&h, c->halo_block));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int ies_halo_ipc_connect(ies_ctx* c, int nbr, const void* handle64) {
+    if (!c || !handle64 || nbr < 0 || nbr > 1) { set_error("ies_halo_ipc_connect: bad argument"); return 1; }
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    if (c->peer_block[nbr]) { cudaIpcCloseMemHandle(c->peer_block[nbr]); c->peer_block[nbr] = nullptr; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* base = nullptr;
+    IES_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_block[nbr] = base;
+    const size_t pbytes = (c->halo_block_bytes - 256) / 4;          // same grid on every rank
+    for (int hf = 0; hf < 2; ++hf) {
+        for (int w = 0; w < 2; ++w) c->peer_recv[nbr][hf][w] = (char*)base + (size_t)(2 * hf + w) * pbytes;
+        c->peer_flag[nbr][hf] = (unsigned*)((char*)base + 4 * pbytes) + 16 * hf;
+    }
+    if (!c->seq_ring) {
+        IES_CUDA(cudaHostAlloc((void**)&c->seq_ring, 4096 * sizeof(unsigned), cudaHostAllocDefault));
+        if (const char* e = getenv("IES_B200_FLAG_MEMCPY")) c->flag_write_mode = atoi(e);
+        if (!drv_entry("cuStreamWriteValue32") || !drv_entry("cuStreamWaitValue32")) c->flag_write_mode = 1;
+    }
+    return 0;
+}
+
+int ies_halo_push(ies_ctx* c, int half) {
+    if (half < 0 || half > 1) { set_error("bad half"); return 1; }
+    // updateH: my first planes go to rank-1 (neighbour 0); updateE: my last planes to rank+1 (neighbour 1)
+    const int nbr = half == IES_HALF_H ? 0 : 1;
+    if (!(nbr == 0 ? c->has_prev : c->has_next)) return 0;
+    if (!c->peer_block[nbr]) { set_error("ies_halo_push: neighbour not connected (ies_halo_ipc_connect)"); return 1; }
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    for (int w = 0; w < 2; ++w) {
+        void* sp; int64_t b;
+        ies_halo_send_ptr(c, half, w, &sp, &b);
+        IES_CUDA(cudaMemcpyAsync(c->peer_recv[nbr][half][w], sp, (size_t)b, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    const unsigned seq = ++c->push_seq[half];
+    if (c->flag_write_mode == 0) {
+        static wait32_fn wr = drv_entry("cuStreamWriteValue32");
+        const int rc = wr(c->stream, (unsigned long long)(uintptr_t)c->peer_flag[nbr][half], seq, 0u);
+        if (rc != 0) { set_error("cuStreamWriteValue32 failed (" + std::to_string(rc) + "); set IES_B200_FLAG_MEMCPY=1"); return 1; }
+    } else {
+        // the ring slot is rewritten 4096 pushes later; the launch queue is far shorter than that
+        unsigned* slot = c->seq_ring + (seq & 4095u);
+        *slot = seq;
+        IES_CUDA(cudaMemcpyAsync(c->peer_flag[nbr][half], slot, sizeof(unsigned), cudaMemcpyHostToDevice, c->stream));
+    }
+    return 0;
+}
+
+int ies_halo_wait(ies_ctx* c, int half) {
+    if (half < 0 || half > 1) { set_error("bad half"); return 1; }
+    // updateH reads the planes of rank+1, updateE those of rank-1
+    if (!(half == IES_HALF_H ? c->has_next : c->has_prev)) return 0;
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    const unsigned seq = ++c->wait_seq[half];
+    static wait32_fn wt = drv_entry("cuStreamWaitValue32");
+    if (!wt) { set_error("cuStreamWaitValue32 is not available in this driver"); return 1; }
+    const int rc = wt(c->stream, (unsigned long long)(uintptr_t)c->halo_flag[half], seq, 1u /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (rc != 0) { set_error("cuStreamWaitValue32 failed (" + std::to_string(rc) + ")"); return 1; }
+    return 0;
+}
+
 int ies_halo_copy(ies_ctx* dst, ies_ctx* src, int half) {
     // order after everything queued on src's stream, run the copies on dst's stream
     IES_CUDA(cudaSetDevice(src->cfg.device));

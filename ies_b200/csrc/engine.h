@@ -64,7 +64,17 @@ struct Ctx {
     int use_ctile;
     int fdtd_vec;               // FDTD: 16-byte vectorised kernel when nz allows (k_fdtd_vec)
     void* scratch[4];           // dzA dzB dxA dxB
-    void* halo_recv[2][2];
+    void* halo_recv[2][2];      // [half][y|z] planes inside halo_block
+    void* halo_block;           // one cudaMalloc: 4 recv planes + the arrival flags (one IPC handle)
+    size_t halo_block_bytes;
+    unsigned* halo_flag[2];     // [half] push counter written by the neighbour (inside halo_block)
+    // inter-process neighbours (CUDA IPC): mapped halo blocks of rank-1 (0) and rank+1 (1)
+    void* peer_block[2];
+    void* peer_recv[2][2][2];   // [nbr][half][y|z] recv planes of that neighbour
+    unsigned* peer_flag[2][2];  // [nbr][half]
+    unsigned push_seq[2], wait_seq[2];
+    unsigned* seq_ring;         // pinned host ring of sequence numbers (memcpy fallback of the flag write)
+    int flag_write_mode;        // 0 = cuStreamWriteValue32, 1 = cudaMemcpyAsync from seq_ring
     void* mult[2][3];           // [half][axis] complex table in FFT precision, pre-scaled by 1/N
     void* tw[3];                // W_N master twiddles per axis
     Box ubox[6];
@@ -84,6 +94,8 @@ struct Ctx {
     unsigned* fused_sync;              // ticket + zdone[nx] + ydone[nx]
     void* fused_ring[2];               // ring scratch (fused_ring_planes planes each) or null
     int fused_ring_alloc;              // planes the ring buffers were allocated for
+    unsigned long long* fused_prof_mem;
+    unsigned long long* fused_prof;    // development: per-phase cycle counters of the fused kernel (option fused_prof) or null
     void* twz_t;                       // z axis: transposed stage tables [forward | inverse] (fft_dev.cuh TwTables)
 };
 

@@ -16,13 +16,26 @@ template <typename T> struct Cx;
 template <> struct Cx<float>  { using type = float2; };
 template <> struct Cx<double> { using type = double2; };
 
-template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
-template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+// Every floating-point operation of the transforms is spelled with an explicit rounding
+// intrinsic: the compiler may then neither contract a*b+c differently in two kernels that
+// inline the same code nor re-associate, so every kernel variant (two-kernel path, fused
+// single-launch path, any dtype instantiation) produces the same bits for the same input.
+__device__ __forceinline__ float  r_add(float a, float b)   { return __fadd_rn(a, b); }
+__device__ __forceinline__ double r_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float  r_sub(float a, float b)   { return __fsub_rn(a, b); }
+__device__ __forceinline__ double r_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float  r_mul(float a, float b)   { return __fmul_rn(a, b); }
+__device__ __forceinline__ double r_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float  r_fma(float a, float b, float c)    { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double r_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { C r; r.x = r_add(a.x, b.x); r.y = r_add(a.y, b.y); return r; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { C r; r.x = r_sub(a.x, b.x); r.y = r_sub(a.y, b.y); return r; }
 template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
-    C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+    C r; r.x = r_fma(a.x, b.x, -r_mul(a.y, b.y)); r.y = r_fma(a.x, b.y, r_mul(a.y, b.x)); return r;
 }
 template <typename C> __device__ __forceinline__ C cmulc(C a, C b) {   // a * conj(b)
-    C r; r.x = a.x * b.x + a.y * b.y; r.y = a.y * b.x - a.x * b.y; return r;
+    C r; r.x = r_fma(a.x, b.x, r_mul(a.y, b.y)); r.y = r_fma(a.y, b.x, -r_mul(a.x, b.y)); return r;
 }
 
 // cos/sin(2*pi*k/16), k = 0..7
@@ -68,8 +81,8 @@ template <int R, bool INV, typename C> struct Dft {
             } else {
                 using Tr = decltype(t.x);
                 const Tr c = (Tr)tw16_cos(k * S), s = (Tr)tw16_sin(k * S);
-                if (INV) { t.x = O[k].x * c - O[k].y * s; t.y = O[k].x * s + O[k].y * c; }
-                else     { t.x = O[k].x * c + O[k].y * s; t.y = O[k].y * c - O[k].x * s; }
+                if (INV) { t.x = r_fma(O[k].x, c, -r_mul(O[k].y, s)); t.y = r_fma(O[k].x, s, r_mul(O[k].y, c)); }
+                else     { t.x = r_fma(O[k].x, c, r_mul(O[k].y, s)); t.y = r_fma(O[k].y, c, -r_mul(O[k].x, s)); }
             }
             out[k]         = cadd(E[k], t);
             out[k + R / 2] = csub(E[k], t);

@@ -22,6 +22,7 @@
 // Arithmetic is the same expression on the same operands as in k_zline + k_yline_update, so the
 // fields are bit-identical to the two-kernel path.
 #pragma once
+#include <algorithm>
 #include "spectral.cuh"
 
 namespace ies {
@@ -33,7 +34,17 @@ struct FusedParams {
     int lead;                   // planes the z role runs ahead of the y role
     int ring;                   // scratch planes (ring > lead; ring >= nx: no wrap)
     int zt, yt;                 // tiles per plane of each role
+    unsigned long long* prof;   // null, or 16 counters of SM cycles per role phase (development: option fused_prof)
 };
+
+// development timers: thread 0 of a CTA adds the cycles since *t0 to prof[slot] and restarts the clock
+__device__ __forceinline__ void fprof(const FusedParams& fp, int slot, long long* t0) {
+    if (fp.prof && threadIdx.x == 0) {
+        const long long t = clock64();
+        atomicAdd(fp.prof + slot, (unsigned long long)(t - *t0));
+        *t0 = t;
+    }
+}
 
 __device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target) {
     if (threadIdx.x == 0) {
@@ -53,26 +64,54 @@ __device__ __forceinline__ void signal_counter(unsigned* ctr) {
 // z role: LPB adjacent z lines of plane pz -> ring slot.  Same transform as k_zline; the
 // exchange buffer is the unpadded swizzled one (64 KB like the y role's stash) and the stage
 // tables come transposed from global memory (twt = [forward stage | inverse stage]).
-template <typename T, bool CPLX, int N>
+// ZM = 0: tables from global memory (L1), unpadded swizzled exchange (64 KB of shared memory);
+// ZM = 1: k_zline's layout -- stage tables + multiplier copied to shared memory, padded exchange.
+template <int N, int ZM> struct FusedZSmem {
+    using TT_ = TwTables<N, 16>;
+    static constexpr int TABLES = (ZM == 1) ? ((TT_::NEED_MASTER ? N : 0) + (TT_::SHARED ? 0 : TT_::FWD) + TT_::INV + N) : 0;
+    static constexpr int LS = (ZM == 1) ? (N + N / 16) : N;
+    static constexpr int ELEMS = TABLES + ZCfg<N, 16>::LPB * LS;      // complex elements
+};
+
+template <typename T, bool CPLX, int N, int ZM, bool SIGNAL = true>
 __device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedParams& fp, const int pz, const int tile,
-                                             typename Cx<T>::type* xbuf,
+                                             typename Cx<T>::type* smem,
                                              const typename Cx<T>::type* __restrict__ tw,
                                              const typename Cx<T>::type* __restrict__ twt,
                                              const typename Cx<T>::type* __restrict__ ml) {
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
-    using X = XchgContigSw<C, N>;
+    using X = typename std::conditional<ZM == 1, XchgContig<C, N>, XchgContigSw<C, N>>::type;
     using TT_ = TwTables<N, 16>;
     constexpr bool TWT = N > 16;
     constexpr int TT = ZCfg<N, 16>::TT, LPB = ZCfg<N, 16>::LPB;
     const C* twf = twt;
     const C* twi = TT_::SHARED ? twt : twt + TT_::FWD;
+    C* xbuf = smem;
+    if constexpr (ZM == 1) {
+        C* s_tw = smem;
+        C* s_twf = s_tw + (TT_::NEED_MASTER ? N : 0);
+        C* s_twi = TT_::SHARED ? s_twf : s_twf + TT_::FWD;
+        C* s_ml = s_twi + TT_::INV;
+        xbuf = s_ml + N;
+        for (int q = threadIdx.x; q < N; q += blockDim.x) {
+            s_ml[q] = ml[q];
+            if (TT_::NEED_MASTER) s_tw[q] = tw[q];
+            if (N > 16) {
+                s_twi[q] = twi[q];
+                if (!TT_::SHARED && q < TT_::FWD) s_twf[q] = twf[q];
+            }
+        }
+        __syncthreads();
+        tw = s_tw; twf = s_twf; twi = s_twi; ml = s_ml;
+    }
     const int t = threadIdx.x % TT, l = threadIdx.x / TT;
     const int row = tile * LPB + l;
     const bool ok = row < p.ny;
     const size_t ibase = ((size_t)pz * p.ny + row) * N;
     const size_t obase = ((size_t)(pz % fp.ring) * p.ny + row) * N;
     X xb{xbuf + (size_t)l * X::LS};
+    long long t0 = fp.prof ? clock64() : 0;
     C v[F::NF][16];
 #pragma unroll
     for (int f = 0; f < F::NF; ++f) {
@@ -86,8 +125,10 @@ __device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedPara
         for (int q = 0; q < 16; ++q) v[f][q] = cmul(v[f][q], ml[spec_index_v<N, 16>(t, q)]);
         fft_inverse_v<N, 16, TWT>(v[f], t, tw, xb, twi);
     }
+    fprof(fp, 0, &t0);
     // the slot's previous tenant (plane pz - ring) must have been consumed
     if (pz - fp.ring >= p.i0) wait_counter(fp.ydone + (pz - fp.ring), (unsigned)fp.yt);
+    fprof(fp, 1, &t0);
     if (ok) {
         void* dA = const_cast<void*>(p.dz[0]);
         void* dB = const_cast<void*>(p.dz[1]);
@@ -97,10 +138,14 @@ __device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedPara
             for (int q = 0; q < 16; ++q) F::st(dA, dB, obase + line_index_v<N, 16>(t, q), v[f][q], f);
         }
     }
-    signal_counter(fp.zdone + pz);
+    if (SIGNAL) signal_counter(fp.zdone + pz);
+    fprof(fp, 2, &t0);
+    if (fp.prof && threadIdx.x == 0) atomicAdd(fp.prof + 8, 1ull);
 }
 
-template <typename T, bool CPLX, int NY, int NZ, bool PAL>
+// YM = 0: the y role reads its twiddle / multiplier tables from global memory (L1), like
+// k_yline_update; YM = 1: it copies them behind the stash in shared memory first (+2N entries).
+template <typename T, bool CPLX, int NY, int NZ, int ZM, int YM>
 __global__ void __launch_bounds__(256, 2)
 k_shpf_fused(const UpdParams p, const FusedParams fp,
              const typename Cx<T>::type* __restrict__ twy, const typename Cx<T>::type* __restrict__ mly,
@@ -111,27 +156,45 @@ k_shpf_fused(const UpdParams p, const FusedParams fp,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* xbuf = reinterpret_cast<C*>(smem_raw);
     __shared__ unsigned s_ticket;
-    if (threadIdx.x == 0) {
-        s_ticket = atomicAdd(fp.ticket, 1u);
-    }
+    // Measured alternatives: persistent CTAs looping over tickets (the loop keeps
+    // both roles' state live: 740 B of spills, 4.3 ms/step); one CTA doing a z tile and then a y
+    // tile (3.05 ms/step: all CTAs run the same phase sequence and the phases overlap less);
+    // tables through L1 instead of shared memory (z FFT 14.6 k cycles per tile instead of 8.5 k,
+    // y FFT 16.2 k instead of 12.6 k).
+    if (threadIdx.x == 0) s_ticket = atomicAdd(fp.ticket, 1u);
     __syncthreads();
     const int per = fp.zt + fp.yt;
     const int g = (int)(s_ticket / (unsigned)per), r = (int)(s_ticket % (unsigned)per);
     const int nplanes = p.i1 - p.i0;
     if (r < fp.zt) {
         if (g >= nplanes) return;
-        fused_z_role<T, CPLX, NZ>(p, fp, p.i0 + g, r, xbuf, twz, twzt, mlz);
+        fused_z_role<T, CPLX, NZ, ZM>(p, fp, p.i0 + g, r, xbuf, twz, twzt, mlz);
     } else {
         const int py = g - fp.lead;
         if (py < 0) return;
         const int i = p.i0 + py;
         const int kb = r - fp.zt;
-        yline_phase_a<T, CPLX, NY>(p, i, kb * YCfg<T, CPLX, NY>::W, xbuf, twy, mly);
+        long long t0 = fp.prof ? clock64() : 0;
+        const C* twy_ = twy;
+        const C* mly_ = mly;
+        if constexpr (YM == 1) {
+            C* s_tw = xbuf + (size_t)NY * YCfg<T, CPLX, NY>::W;
+            C* s_ml = s_tw + NY;
+            for (int q = threadIdx.x; q < NY; q += blockDim.x) { s_tw[q] = twy[q]; s_ml[q] = mly[q]; }
+            __syncthreads();
+            twy_ = s_tw; mly_ = s_ml;
+        }
+        yline_phase_a<T, CPLX, NY>(p, i, kb * YCfg<T, CPLX, NY>::W, xbuf, twy_, mly_);
+        fprof(fp, 3, &t0);
         wait_counter(fp.zdone + i, (unsigned)fp.zt);     // also the barrier that publishes the stash
+        fprof(fp, 4, &t0);
         const long long plane = (long long)p.ny * p.nz;
         const long long dz_off = ((long long)(i % fp.ring) - (long long)i) * plane;
-        yline_phase_b_dispatch<T, CPLX, NY, PAL>(p, i, kb, fp.yt, xbuf, dz_off);
-        signal_counter(fp.ydone + i);
+        yline_phase_b_dispatch<T, CPLX, NY, false>(p, i, kb, fp.yt, xbuf, dz_off);
+        // only a z tile that re-uses this plane's ring slot waits for it
+        if (i + fp.ring < p.i1) signal_counter(fp.ydone + i);
+        fprof(fp, 5, &t0);
+        if (fp.prof && threadIdx.x == 0) atomicAdd(fp.prof + 9, 1ull);
     }
 }
 
@@ -145,18 +208,20 @@ int launch_shpf_fused(Ctx* c, const UpdParams& p, int half) {
         const int ny = c->cfg.ny, nz = c->cfg.nz;
         if (ny != nz) return 2;
         if (p.i1 <= p.i0) return 0;
-        const bool pal = p.Cidx != nullptr;
+        if (p.Cidx != nullptr) return 2;            // palette-form coefficients: two-kernel path
         FusedParams fp;
         fp.ticket = c->fused_sync; fp.zdone = c->fused_sync + 1; fp.ydone = c->fused_sync + 1 + c->cfg.nx;
         fp.lead = c->fused_lead;
         fp.ring = c->fused_ring_planes;
+        fp.prof = c->fused_prof;
         IES_CUDA(cudaMemsetAsync(c->fused_sync, 0, sizeof(unsigned) * (size_t)(1 + 2 * c->cfg.nx), c->stream));
         const int nplanes = p.i1 - p.i0;
 #define F_CASE(NN) {                                                                        \
             fp.zt = (ny + ZCfg<NN, 16>::LPB - 1) / ZCfg<NN, 16>::LPB;                       \
             fp.yt = (nz + YCfg<T, CPLX, NN>::W - 1) / YCfg<T, CPLX, NN>::W;                  \
-            const size_t sm = sizeof(C) * (size_t)NN * YCfg<T, CPLX, NN>::W;                 \
-            auto kern = pal ? k_shpf_fused<T, CPLX, NN, NN, true> : k_shpf_fused<T, CPLX, NN, NN, false>; \
+            const size_t sm0 = sizeof(C) * (size_t)NN * YCfg<T, CPLX, NN>::W;                \
+            const size_t sm = std::max(sizeof(C) * (size_t)FusedZSmem<NN, 1>::ELEMS, sm0 + sizeof(C) * 2 * NN); \
+            auto kern = k_shpf_fused<T, CPLX, NN, NN, 1, 1>;                                \
             if (set_smem(kern, sm)) return 1;                                               \
             const unsigned grid = (unsigned)((nplanes + fp.lead) * (fp.zt + fp.yt));        \
             kern<<<grid, 256, sm, c->stream>>>(p, fp, (const C*)c->tw[1], (const C*)c->mult[half][1], \

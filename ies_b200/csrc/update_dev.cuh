@@ -11,13 +11,16 @@ template <bool CPLX> struct AccT;
 template <> struct AccT<false> { using type = double; };
 template <> struct AccT<true>  { using type = double2; };
 
-__device__ __forceinline__ double  a_add(double a, double b) { return a + b; }
-__device__ __forceinline__ double  a_sub(double a, double b) { return a - b; }
-__device__ __forceinline__ double  a_scale(double s, double a) { return s * a; }
+// Explicitly rounded (never contracted into FMAs): the update is then the reference's own
+// NumPy expression -- one rounding per multiply / add / subtract, space.py:801-803 -- and gives
+// the same bits in every kernel that inlines it.
+__device__ __forceinline__ double  a_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double  a_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double  a_scale(double s, double a) { return __dmul_rn(s, a); }
 __device__ __forceinline__ double  a_zero(double) { return 0.0; }
-__device__ __forceinline__ double2 a_add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ double2 a_sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ double2 a_scale(double s, double2 a) { return make_double2(s * a.x, s * a.y); }
+__device__ __forceinline__ double2 a_add(double2 a, double2 b) { return make_double2(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y)); }
+__device__ __forceinline__ double2 a_sub(double2 a, double2 b) { return make_double2(__dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y)); }
+__device__ __forceinline__ double2 a_scale(double s, double2 a) { return make_double2(__dmul_rn(s, a.x), __dmul_rn(s, a.y)); }
 __device__ __forceinline__ double2 a_zero(double2) { return make_double2(0.0, 0.0); }
 
 template <typename T, bool CPLX> struct Elem;

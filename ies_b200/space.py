@@ -652,9 +652,10 @@ class Basic3D:
         self._half_step(_lib.HALF_E, tstep)
 
     def _half_step(self, half, tstep):
-        """Halo exchange + update.  A comm with exchange_begin/exchange_end (TorchComm) runs the
-        transfer on its own stream while the engine does the part of the half-step that needs
-        no neighbour plane (the z-line derivative pass); the rest waits for the halo event."""
+        """Halo exchange + update.  IpcComm / LocalComm only ENQUEUE the transfer (copy engine) and the
+        stream-ordered wait in front of the update; nothing blocks the host.  A communicator with
+        exchange_begin/exchange_end (tests/torch_comm.TorchComm) runs its transfer on its own stream
+        while the engine does the part of the half-step that needs no neighbour plane."""
         comm = self.MPIcomm
         if self.MPIsize > 1 and hasattr(comm, 'exchange_begin'):
             token = comm.exchange_begin(self, half)

@@ -74,8 +74,10 @@ int ies_destroy(ies_ctx* ctx);
 int ies_set_stream(ies_ctx* ctx, void* cuda_stream);
 int ies_sync(ies_ctx* ctx);
 /* Engine tuning knobs (no reference counterpart; defaults need no call).  Names:
- * "split" (1 = SHPF cell update split between the z-line and the y-line kernel [default],
- * 0 = z-line derivative kernel + full y-line update kernel), "palette" (1 = palette-compressed coefficient arrays
+ * "fused" (SHPF, real dtypes, ny == nz in {64,128,256,512}: 1 = the half-step as one launch,
+ * z-line and y-line tiles as two roles of one grid [shpf_fused.cuh]; 0 = z-line derivative kernel +
+ * y-line update kernel), "fused_lead" (planes the z role runs ahead), "fused_ring" (scratch ring
+ * size in planes, 0 = full-size scratch), "palette" (1 = palette-compressed coefficient arrays
  * when they hold <= 32 distinct values; default 0), "reset_psi" (zero the CPML auxiliary
  * arrays). */
 int ies_set_option(ies_ctx* ctx, const char* name, int64_t value);
@@ -121,6 +123,21 @@ int ies_halo_recv_ptr(ies_ctx* ctx, int half, int which, void** dev, int64_t* by
  * copies src's send planes into dst's recv planes with cudaMemcpyPeerAsync,
  * ordered after src's stream and before dst's next update. */
 int ies_halo_copy(ies_ctx* dst, ies_ctx* src, int half);
+/* One process per GPU (the reference's `mpirun -n R`): the blocking pickled mpi4py send/recv of
+ * space.py:645-670, 863-887 becomes copy-engine transfers over NVLink into peer-mapped memory.
+ *   ies_halo_ipc_export : 64-byte CUDA IPC handle of this slab's receive planes + arrival flags;
+ *   ies_halo_ipc_connect: map a neighbour's handle (nbr 0 = rank-1, 1 = rank+1);
+ *   ies_halo_push(half) : enqueue the copy of my two send planes (half H: Ey[0],Ez[0] -> rank-1,
+ *                         half E: Hy[-1],Hz[-1] -> rank+1) into that neighbour's receive planes and,
+ *                         in stream order after them, the write of the push count to its flag;
+ *   ies_halo_wait(half) : enqueue a stream memory wait (flag >= my wait count) in front of the
+ *                         update that reads the planes.
+ * Every updateH / updateE of a slab with a neighbour does one push and one wait; nothing blocks
+ * the host and no kernel runs for the exchange. */
+int ies_halo_ipc_export(ies_ctx* ctx, void* handle64);
+int ies_halo_ipc_connect(ies_ctx* ctx, int nbr, const void* handle64);
+int ies_halo_push(ies_ctx* ctx, int half);
+int ies_halo_wait(ies_ctx* ctx, int half);
 
 /* Setter.put_src (source.py:167-253): F[lo:hi] (+)= pulse * px[i]*py[j]*pz[k].
  * px/py/pz are complex128 (re,im) tables of the box extents or NULL (=1). */
@@ -165,6 +182,10 @@ int ies_timer_stop(ies_ctx* ctx, double* ms);
  * (PSTD), 3 = FDTD update. */
 int ies_profile(ies_ctx* ctx, int on);
 int ies_profile_read(ies_ctx* ctx, int slot, double* ms_total, int64_t* launches);
+/* Development: SM-cycle totals per phase of the fused SHPF kernel since ies_set_option("fused_prof", 1):
+ * [0] z FFT, [1] z ring wait, [2] z store+signal, [3] y FFT, [4] y wait for z, [5] y update,
+ * [8] z tiles, [9] y tiles. */
+int ies_fused_prof_read(ies_ctx* ctx, uint64_t* out16);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,17 @@ import types
 
 import numpy as np
 
-REF = os.environ.get('IES_REFERENCE_DIR', '/root/reference')
+def _ref_dir():
+    # the reference where it lies in the build container, else the copy oracle/make_ref.py
+    # placed under oracle/_ref/ (travels to the GPU box; never committed)
+    for d in (os.environ.get('IES_REFERENCE_DIR'), '/root/reference',
+              os.path.join(os.path.dirname(os.path.abspath(__file__)), '_ref')):
+        if d and os.path.isfile(os.path.join(d, 'space.py')):
+            return d
+    return '/root/reference'
+
+
+REF = _ref_dir()
 
 
 def reference_available():
@@ -139,7 +149,7 @@ def load_reference():
     if 'ns' in _cache:
         return _cache['ns']
     if not reference_available():
-        raise RuntimeError('/root/reference is not present on this machine')
+        raise RuntimeError('the reference is not present on this machine (/root/reference or oracle/_ref)')
     _install_shims()
     ns = types.SimpleNamespace()
     for name in ('space', 'source', 'collector', 'structure'):

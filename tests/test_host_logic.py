@@ -156,8 +156,8 @@ def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    from ies_b200 import comm
-    tc = comm.TorchComm()
+    from tests import torch_comm
+    tc = torch_comm.TorchComm()
     ok = True
     for step in range(3):
         first = [torch.full((4, 5), float(100 * rank + step)), torch.full((4, 5), float(100 * rank + step + 0.5))]
@@ -184,7 +184,8 @@ def _gloo_worker(rank, world, port, q):
 
 @pytest.mark.parametrize('world', [2, 3])
 def test_torchcomm_exchange_pattern_gloo(world):
-    """N > 1 plumbing on CPU: the neighbour send/recv pattern of comm.TorchComm over gloo."""
+    """N > 1 plumbing on CPU: the neighbour send/recv pattern (first planes to rank-1 before
+    updateH, last planes to rank+1 before updateE) over gloo, tests/torch_comm.TorchComm."""
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
@@ -192,5 +193,83 @@ def test_torchcomm_exchange_pattern_gloo(world):
     ps = [ctx.Process(target=_gloo_worker, args=(r, world, port, q)) for r in range(world)]
     [p.start() for p in ps]
     res = [q.get(timeout=180) for _ in ps]
+    [p.join(60) for p in ps]
+    assert all(ok for _, ok in res), res
+
+
+class _FakeHaloLib:
+    """CPU stand-in for the four ies_halo_* entry points IpcComm drives: a 'handle' is the rank
+    number, a push appends (half, seq) to a file of the neighbour it targets, a wait records what
+    the rank expects.  Lets the connect / push / wait call pattern run without a GPU."""
+
+    def __init__(self, rank, size, tmp):
+        self.rank, self.size, self.tmp = rank, size, tmp
+        self.peers, self.seq, self.waits = {}, [0, 0], []
+
+    def ies_halo_ipc_export(self, ctx, h):
+        h[0] = self.rank + 1
+        return 0
+
+    def ies_halo_ipc_connect(self, ctx, nbr, h):
+        self.peers[nbr] = int(h[0]) - 1
+        return 0
+
+    def ies_halo_push(self, ctx, half):
+        nbr = 0 if half == 0 else 1
+        if nbr in self.peers:
+            self.seq[half] += 1
+            with open(os.path.join(self.tmp, f'to{self.peers[nbr]}_half{half}'), 'a') as f:
+                f.write(f'{self.rank} {self.seq[half]}\n')
+        return 0
+
+    def ies_halo_wait(self, ctx, half):
+        src = self.rank + 1 if half == 0 else self.rank - 1
+        if 0 <= src < self.size:
+            self.waits.append((half, src))
+        return 0
+
+    def ies_last_error(self): return b''
+
+
+def _ipc_worker(rank, world, port, tmp, q):
+    import types
+    from ies_b200 import comm, _lib
+    fake = _FakeHaloLib(rank, world, tmp)
+    _lib._lib = fake                                   # IpcComm calls _lib.load()
+    c = comm.IpcComm(rank, world, comm.SocketStore(rank, world, port=port))
+    spaces = [types.SimpleNamespace(_ctx=None), types.SimpleNamespace(_ctx=None)]     # TF and IF
+    for step in range(3):
+        for sp in spaces: c.exchange(sp, 0)
+        for sp in spaces: c.exchange(sp, 1)
+    c.Barrier()
+    g = c.gather(np.full(3, rank), root=0)
+    ok = fake.peers == {n: r for n, r in ((0, rank - 1), (1, rank + 1)) if 0 <= r < world}
+    exp_waits = [(h, s) for h, s in ((0, rank + 1), (1, rank - 1)) if 0 <= s < world]
+    ok &= fake.waits == [w for _ in range(3) for w in ([x for x in exp_waits if x[0] == 0] * 2 + [x for x in exp_waits if x[0] == 1] * 2)]
+    if rank == 0:
+        ok &= [int(a[0]) for a in g] == list(range(world))
+    c.Barrier()
+    # what arrived for me: half 0 pushes come from rank+1, half 1 pushes from rank-1, 6 each (2 spaces x 3 steps)
+    for half, src in ((0, rank + 1), (1, rank - 1)):
+        path = os.path.join(tmp, f'to{rank}_half{half}')
+        if 0 <= src < world:
+            rows = [l.split() for l in open(path)]
+            ok &= len(rows) == 6 and all(int(r[0]) == src for r in rows)
+        else:
+            ok &= not os.path.exists(path)
+    q.put((rank, bool(ok)))
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_ipccomm_rendezvous_and_exchange_pattern(world, tmp_path):
+    """N > 1 plumbing on CPU: SocketStore rendezvous (set/get/barrier/gather over TCP) and the
+    export -> connect -> push -> wait sequence IpcComm drives, against a fake halo library."""
+    import multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 30600 + world + (os.getpid() % 200)
+    ps = [ctx.Process(target=_ipc_worker, args=(r, world, port, str(tmp_path), q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in ps]
     [p.join(60) for p in ps]
     assert all(ok for _, ok in res), res

@@ -21,7 +21,7 @@ def main():
     lib = _lib.load()
     ns = types.SimpleNamespace(space=ies_b200.space, source=ies_b200.source,
                                structure=ies_b200.structure, collector=ies_b200.collector)
-    sp, setter, src = bench.build_space(ns, 1024, 100000)
+    sp, setter, src = bench.build_space(ns, bench.WORKLOADS['headline'], 1, 100000)
     sp.init_update_constants()
     rng = np.random.default_rng(7)
     for n in ('Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz'):

@@ -23,24 +23,21 @@ import bench  # noqa: E402
 
 VARIANTS = [
     ('base', dict(fused=0)),                            # two-kernel path (k_zline + k_yline_update)
-    ('fused_full_l3', dict(fused=1, fused_ring=0, fused_lead=3)),     # single launch, full-size scratch
-    ('fused_full_l1', dict(fused=1, fused_ring=0, fused_lead=1)),
-    ('fused_full_l8', dict(fused=1, fused_ring=0, fused_lead=8)),
-    ('fused_r16_l3', dict(fused=1, fused_ring=16, fused_lead=3)),     # scratch ring of 16 planes (16 MiB)
-    ('fused_r32_l3', dict(fused=1, fused_ring=32, fused_lead=3)),
-    ('fused_r32_l8', dict(fused=1, fused_ring=32, fused_lead=8)),
-    ('fused_r64_l3', dict(fused=1, fused_ring=64, fused_lead=3)),
-    ('fused_r8_l2', dict(fused=1, fused_ring=8, fused_lead=2)),
+    ('fused', dict(fused=1)),                           # single launch, full-size scratch, lead 3
+    ('fused_l1', dict(fused=1, fused_lead=1)),
+    ('fused_l6', dict(fused=1, fused_lead=6)),
+    ('fused_r32', dict(fused=1, fused_ring=32)),        # scratch ring of 32 planes
     ('noctile', dict(fused=0, ctile=0)),
     ('palette', dict(fused=0, palette=1, ctile=0)),
 ]
 ALL_OPTS = ('fused', 'fused_ring', 'fused_lead', 'palette', 'ctile')
-DEFAULTS = dict(fused=0, fused_ring=0, fused_lead=3, palette=0, ctile=1)
+DEFAULTS = dict(fused=1, fused_ring=0, fused_lead=3, palette=0, ctile=1)
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--nx', type=int, default=1024)
+    ap.add_argument('--nx', type=int, default=0)
+    ap.add_argument('--config', default='headline')
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--only', default='')
@@ -55,12 +52,13 @@ def main():
     lib = _lib.load()
     ns = types.SimpleNamespace(space=ies_b200.space, source=ies_b200.source,
                                structure=ies_b200.structure, collector=ies_b200.collector)
-    bench.NX_PER_GPU = args.nx
-    sp, setter, src = bench.build_space(ns, args.nx, 100000)
+    wl = bench.WORKLOADS[args.config]
+    g1 = bench.grid_of(wl, 1)
+    sp, setter, src = bench.build_space(ns, wl, 1, 100000, grid=(args.nx if args.nx else g1[0], g1[1], g1[2]))
     sp.init_update_constants()
     rng = np.random.default_rng(7)
     init = {n: rng.uniform(-1, 1, sp.loc_grid) for n in ('Ex', 'Ey', 'Ez', 'Hx', 'Hy', 'Hz')}
-    ncell = sp.myNx * bench.NY * bench.NZ
+    ncell = sp.myNx * g1[1] * g1[2]
 
     def upload():
         _lib.check(lib.ies_set_option(sp._ctx, b'reset_psi', 1))
@@ -112,6 +110,15 @@ def main():
             _lib.check(lib.ies_timer_stop(sp._ctx, C.byref(ms)))
             sp.sync()
             per = ms.value / max(args.steps, 1)
+            if o.get('fused'):
+                _lib.check(lib.ies_set_option(sp._ctx, b'fused_prof', 1))
+                for t in range(2): step(t)
+                pr = (C.c_uint64 * 16)()
+                _lib.check(lib.ies_fused_prof_read(sp._ctx, pr))
+                _lib.check(lib.ies_set_option(sp._ctx, b'fused_prof', 0))
+                nz_, ny_ = max(pr[8], 1), max(pr[9], 1)
+                print('  cycles/tile: z fft %d, z ringwait %d, z store %d | y fft %d, y wait %d, y update %d' % (
+                    pr[0] // nz_, pr[1] // nz_, pr[2] // nz_, pr[3] // ny_, pr[4] // ny_, pr[5] // ny_), flush=True)
             row = dict(name=name, ms_per_step=round(per, 4), gcell_s=round(ncell / per / 1e6, 2) if per > 0 else None,
                        bit_identical=sig_ok, opts=o)
         except Exception as e:      # keep sweeping
