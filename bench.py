@@ -64,6 +64,13 @@ WORKLOADS = {
 }
 
 
+# development workloads (tools/kexp.py --config ...): separate the line-length and the CPML effects
+WORKLOADS['x512'] = dict(WORKLOADS['headline'], per_gpu=(256, 512, 512), gap=(720 * um / 256, 1 * um, 1 * um),
+                         metric="Mcell-updates/s (fp64 SHPF 256x512x512 per GPU, CPML-x)")
+WORKLOADS['all256'] = dict(WORKLOADS['mie'], per_gpu=(1024, 256, 256),
+                           metric="Mcell-updates/s (fp64 SHPF 1024x256x256 per GPU, CPML on all faces)")
+
+
 def grid_of(wl, world):
     if 'per_gpu' in wl:
         nx, ny, nz = wl['per_gpu']

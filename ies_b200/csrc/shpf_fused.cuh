@@ -46,10 +46,14 @@ __device__ __forceinline__ void fprof(const FusedParams& fp, int slot, long long
     }
 }
 
-__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target) {
+// FENCE: acquire fence after the poll.  Needed when the data behind the counter may sit stale in
+// this SM's L1 (a re-used ring slot); with a full-size scratch every line is read by exactly one
+// CTA per launch and L1 starts every launch empty, so the poll + barrier order the loads and the
+// fence (an L1 invalidation for the whole SM, also for the CTA next door) is skipped.
+__device__ __forceinline__ void wait_counter(const unsigned* ctr, unsigned target, bool fence) {
     if (threadIdx.x == 0) {
-        while (*(volatile const unsigned*)ctr < target) __nanosleep(100);
-        __threadfence();        // acquire: also drops this SM's stale L1 lines of a reused ring slot
+        while (*(volatile const unsigned*)ctr < target) __nanosleep(20);
+        if (fence) __threadfence();
     }
     __syncthreads();
 }
@@ -127,7 +131,7 @@ __device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedPara
     }
     fprof(fp, 0, &t0);
     // the slot's previous tenant (plane pz - ring) must have been consumed
-    if (pz - fp.ring >= p.i0) wait_counter(fp.ydone + (pz - fp.ring), (unsigned)fp.yt);
+    if (pz - fp.ring >= p.i0) wait_counter(fp.ydone + (pz - fp.ring), (unsigned)fp.yt, true);
     fprof(fp, 1, &t0);
     if (ok) {
         void* dA = const_cast<void*>(p.dz[0]);
@@ -186,7 +190,7 @@ k_shpf_fused(const UpdParams p, const FusedParams fp,
         }
         yline_phase_a<T, CPLX, NY>(p, i, kb * YCfg<T, CPLX, NY>::W, xbuf, twy_, mly_);
         fprof(fp, 3, &t0);
-        wait_counter(fp.zdone + i, (unsigned)fp.zt);     // also the barrier that publishes the stash
+        wait_counter(fp.zdone + i, (unsigned)fp.zt, fp.ring < p.i1 - p.i0);     // also the barrier that publishes the stash
         fprof(fp, 4, &t0);
         const long long plane = (long long)p.ny * p.nz;
         const long long dz_off = ((long long)(i % fp.ring) - (long long)i) * plane;
