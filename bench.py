@@ -337,7 +337,30 @@ def run_reference_arm(args, rank, world):
 
 
 # ------------------------------------------------------------------ GPU arm
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Point fd 1 at stderr for the rest of the run (NCCL and the API mirror's set-up messages print
+    from C and Python); emit() writes the ONE JSON line to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 def run_b200(args, rank, world, local_rank):
+    quiet_stdout()
     import torch
     from ies_b200 import _lib, comm as icomm
     ns = product_ns()
@@ -534,7 +557,7 @@ def run_b200(args, rank, world, local_rank):
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None: dist.destroy_process_group()
 
 

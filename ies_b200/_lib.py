@@ -55,7 +55,7 @@ SIGNATURES = {
     'ies_device_count': (C.c_int, [C.POINTER(C.c_int)]),
     'ies_create': (C.c_int, [C.POINTER(Config), C.POINTER(_vp)]),
     'ies_destroy': (C.c_int, [_vp]),
-    'ies_set_stream': (C.c_int, [_vp, _vp]),
+    'ies_set_stream': (C.c_int, [_vp, _vp, C.c_int]),
     'ies_sync': (C.c_int, [_vp]),
     'ies_set_option': (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     'ies_set_coeff': (C.c_int, [_vp, C.c_int, _dp, C.c_int64]),

@@ -12,9 +12,10 @@ import os
 import numpy as np
 
 try:
-    from . import _lib
+    from . import _lib, comm as _comm
 except ImportError:
     import _lib
+    import comm as _comm
 
 
 def _pair(space):
@@ -39,26 +40,8 @@ class collector:
         self.lloc = None
 
     def _get_local_x_loc(self, gxsrts, gxends):
-        """collector.py:30-118."""
-        assert gxsrts >= 0
-        assert gxends < self.space.Nx
-        bxsrt = self.space.myNx_indice[self.space.MPIrank][0]
-        bxend = self.space.myNx_indice[self.space.MPIrank][1]
-        gxloc = None
-        lxloc = None
-        if gxsrts >= bxsrt and gxsrts < bxend and gxends <= bxend:
-            gxloc = (gxsrts, gxends)
-            lxloc = (gxsrts - bxsrt, gxends - bxsrt)
-        if gxsrts >= bxsrt and gxsrts < bxend and gxends > bxend:
-            gxloc = (gxsrts, bxend)
-            lxloc = (gxsrts - bxsrt, bxend - bxsrt)
-        if gxsrts < bxsrt and gxends > bxend:
-            gxloc = (bxsrt, bxend)
-            lxloc = (bxsrt - bxsrt, bxend - bxsrt)
-        if gxsrts < bxsrt and gxends > bxsrt and gxends <= bxend:
-            gxloc = (bxsrt, gxends)
-            lxloc = (bxsrt - bxsrt, gxends - bxsrt)
-        return gxloc, lxloc
+        """collector.py:30-118: the one shared statement of the rule lives in comm.local_x_loc."""
+        return _comm.local_x_loc(self.space, gxsrts, gxends)
 
     # ---- device DFT plumbing shared by Sx/Sy/Sz
     def _ensure(self):

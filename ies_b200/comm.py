@@ -24,6 +24,21 @@ except ImportError:  # imported as a top-level module (sys.path drop-in)
     import _lib
 
 
+def local_x_loc(space, gxsrts, gxends):
+    """Clip a global x range [gxsrts, gxends) to this rank's slab: (global range, local range) or
+    (None, None).  ONE statement of the rule of structure.py:17-107 and collector.py:30-118 (the
+    reference carries two copies): interval-overlap cases written as one intersection."""
+    assert gxsrts >= 0
+    assert gxends < space.Nx
+    bxsrt, bxend = space.myNx_indice[space.MPIrank]
+    lo, hi = max(gxsrts, bxsrt), min(gxends, bxend)
+    # a zero-length request (gxsrts == gxends) belongs to the slab that contains gxsrts
+    if (gxsrts == gxends and bxsrt <= gxsrts < bxend) or lo < hi:
+        hi = max(hi, lo)
+        return (lo, hi), (lo - bxsrt, hi - bxsrt)
+    return None, None
+
+
 class SingleComm:
     rank, size = 0, 1
 

@@ -575,6 +575,8 @@ int64_t ies_launch_count(void) { return g_launches.load(); }
 
 int ies_device_count(int* n) { IES_CUDA(cudaGetDeviceCount(n)); return 0; }
 
+static int create_impl(const ies_config* cfg, ies_ctx* c);
+
 int ies_create(const ies_config* cfg, ies_ctx** out) {
     if (!cfg || !out) { set_error("null argument"); return 1; }
     if (cfg->nx < 1 || cfg->ny < 2 || cfg->nz < 2) { set_error("bad grid"); return 1; }
@@ -592,6 +594,21 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     if (cfg->device < 0 || cfg->device >= ndev) { set_error("no such CUDA device"); return 1; }
     IES_CUDA(cudaSetDevice(cfg->device));
     ies_ctx* c = new ies_ctx();
+    c->own_stream = nullptr; c->ev_halo = nullptr; c->ev_t0 = c->ev_t1 = nullptr;
+    c->stage = nullptr; c->stage_bytes = 0; c->seq_ring = nullptr;
+    c->peer_block[0] = c->peer_block[1] = nullptr;
+    if (create_impl(cfg, c)) {              // the error text survives the clean-up
+        const std::string keep = ies_last_error();
+        if (c->own_stream) { c->stream = c->own_stream; ies_destroy(c); }
+        else { for (void* p : c->owned) cudaFree(p); delete c; }
+        set_error(keep);
+        return 1;
+    }
+    *out = c;
+    return 0;
+}
+
+static int create_impl(const ies_config* cfg, ies_ctx* c) {
     c->cfg = *cfg;
     c->cplx = cfg->dtype >= 2;
     c->dbl = (cfg->dtype & 1) != 0;
@@ -686,9 +703,7 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     for (int a = 0; a < 3; ++a) c->ghost_on[a] = 0;
     c->has_prev = cfg->rank > 0;
     c->has_next = cfg->rank < cfg->nranks - 1;
-    c->stage = nullptr; c->stage_bytes = 0;
     IES_CUDA(cudaStreamSynchronize(c->stream));
-    *out = c;
     return 0;
 }
 
@@ -700,7 +715,9 @@ int ies_destroy(ies_ctx* c) {
     if (c->stage) cudaFree(c->stage);
     for (int n = 0; n < 2; ++n) if (c->peer_block[n]) cudaIpcCloseMemHandle(c->peer_block[n]);
     if (c->seq_ring) cudaFreeHost(c->seq_ring);
-    cudaEventDestroy(c->ev_halo);
+    if (c->ev_halo) cudaEventDestroy(c->ev_halo);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return 0;
@@ -733,12 +750,15 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     return 0;
 }
 
-int ies_set_stream(ies_ctx* c, void* s) {
+int ies_set_stream(ies_ctx* c, void* s, int use_own_stream) {
     // work already queued on the old stream (set-up, a source injection) must be visible to
     // whatever is enqueued on the new one
+    if (!c) { set_error("null context"); return 1; }
     IES_CUDA(cudaSetDevice(c->cfg.device));
     IES_CUDA(cudaStreamSynchronize(c->stream));
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    // an external handle of 0 is the legacy default stream of the caller -- a legitimate choice
+    // (e.g. torch's default stream), not a request for the context's own stream
+    c->stream = use_own_stream ? c->own_stream : (cudaStream_t)s;
     return 0;
 }
 int ies_timer_start(ies_ctx* c) {
@@ -858,7 +878,22 @@ int ies_set_multiplier(ies_ctx* c, int half, int axis, const double* re_im, int3
     return 0;
 }
 
-int ies_clear_pml(ies_ctx* c) { c->terms[0].clear(); c->terms[1].clear(); return 0; }
+int ies_clear_pml(ies_ctx* c) {
+    // the psi arrays and profile tables of the dropped terms go back to the allocator
+    IES_CUDA(cudaSetDevice(c->cfg.device));
+    IES_CUDA(cudaStreamSynchronize(c->stream));
+    for (int h = 0; h < 2; ++h) {
+        for (const PmlTermDev& t : c->terms[h]) {
+            void* ptrs[2] = {t.psi, const_cast<double*>(t.b)};       // b, a, kf share one allocation
+            for (void* q : ptrs) {
+                auto it = std::find(c->owned.begin(), c->owned.end(), q);
+                if (it != c->owned.end()) { cudaFree(q); c->owned.erase(it); }
+            }
+        }
+        c->terms[h].clear();
+    }
+    return 0;
+}
 
 int ies_add_pml_term(ies_ctx* c, const ies_pml_term* t) {
     if (!t || t->half < 0 || t->half > 1 || t->comp < 0 || t->comp > 2 || t->diff < 0 || t->diff > 5 || t->axis < 0 || t->axis > 2) {

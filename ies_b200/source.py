@@ -1,8 +1,10 @@
 """source.Setter and the pulse shapes on the b200 engine (reference: source.py).
 
 Index logic (Python banker's `round`, the zero-length-x decrement, the owning
-rank) is restated bit-exactly from source.py:57-128; the injection itself is one
-small kernel on the device (ies_put_src) instead of a sliced `+=` on the array.
+rank) is a line-by-line restatement of source.py:57-165 -- the host API mirror, whose
+integers must equal the reference's -- and the pulse classes keep the reference's formulas;
+the injection itself is one small kernel on the device (ies_put_src) instead of a sliced
+`+=` on the array.
 """
 import numpy as np
 from scipy.constants import c, mu_0, epsilon_0
@@ -86,23 +88,36 @@ class Setter:
             return
         if put_type not in ('soft', 'hard'):
             raise ValueError("Please insert 'soft' or 'hard'")
-        name = where[0].upper() + where[1].lower()
-        if name not in _lib.COMP:
-            return      # the reference silently ignores unknown field names
+        # the reference compares with exactly two spellings per component, 'Ex' / 'ex'
+        # (source.py:236-251), and silently ignores anything else
+        if where not in _lib.COMP and not (len(where) == 2 and where[0] in 'eh' and where[1] in 'xyz'):
+            return
+        name = where[0].upper() + where[1]
         sp = self.space
-        lo = (self.my_src_xsrt, self.src_ysrt, self.src_zsrt)
-        hi = (self.my_src_xend, self.src_yend, self.src_zend)
+        # NumPy slice semantics of `F[x0:x1, y0:y1, z0:z1]`: extents are clamped to the array and an
+        # inverted range is empty
+        rng = [slice(a, b).indices(n) for a, b, n in ((self.my_src_xsrt, self.my_src_xend, sp.loc_grid[0]),
+                                                       (self.src_ysrt, self.src_yend, sp.loc_grid[1]),
+                                                       (self.src_zsrt, self.src_zend, sp.loc_grid[2]))]
+        lo = tuple(r[0] for r in rng)
+        hi = tuple(max(r[0], r[1]) for r in rng)
+        if any(h <= l for l, h in zip(lo, hi)):
+            return
         real_field = np.dtype(sp.field_dtype).kind != 'c'
-        if real_field and (isinstance(pulse, complex) or np.iscomplexobj(pulse)) and put_type == 'soft':
-            # what `real_array[...] += complex` does in NumPy
-            raise TypeError("Cannot cast ufunc 'add' output from dtype('complex128') to "
-                            f"dtype('{np.dtype(sp.field_dtype).name}') with casting rule 'same_kind'")
+        if real_field and (isinstance(pulse, complex) or np.iscomplexobj(pulse)):
+            # what `real_array[...] += complex` / `real_array[...] = complex` do in NumPy
+            if put_type == 'soft':
+                raise TypeError("Cannot cast ufunc 'add' output from dtype('complex128') to "
+                                f"dtype('{np.dtype(sp.field_dtype).name}') with casting rule 'same_kind'")
+            raise TypeError("float() argument must be a string or a real number, not 'complex'")
         pv = complex(pulse)
         px = py = pz = None
         if sp.BBC_called == True:
-            px = np.ascontiguousarray(self.px, dtype=np.complex128)
-            py = np.ascontiguousarray(self.py, dtype=np.complex128)
-            pz = np.ascontiguousarray(self.pz, dtype=np.complex128)
+            # phase tables cut to the clamped box (they are indexed from the unclamped start)
+            cut = lambda t, l, h, s0: (t if t.size == 1 else t[l - s0:h - s0])
+            px = np.ascontiguousarray(cut(self.px, lo[0], hi[0], self.my_src_xsrt), dtype=np.complex128)
+            py = np.ascontiguousarray(cut(self.py, lo[1], hi[1], self.src_ysrt), dtype=np.complex128)
+            pz = np.ascontiguousarray(cut(self.pz, lo[2], hi[2], self.src_zsrt), dtype=np.complex128)
             self._keep = (px, py, pz)
         vp = lambda a: None if a is None else a.ctypes.data
         _lib.check(sp._lib.ies_put_src(sp._ctx, _lib.COMP[name], _lib.I3(*lo), _lib.I3(*hi),

@@ -232,12 +232,9 @@ class Basic3D:
         if self.device is None:
             self.device = _comm.default_device(self.MPIcomm)
         self._lib = _lib.load()
-        cfg = _lib.Config(self.myNx, self.Ny, self.Nz, _lib.DTYPE_CODE[np.dtype(self.field_dtype)],
-                          _lib.METHOD_CODE[self.method], self.MPIrank, self.MPIsize, int(self.device),
-                          self.dx, self.dy, self.dz, self.dt)
-        ctx = C.c_void_p()
-        _lib.check(self._lib.ies_create(C.byref(cfg), C.byref(ctx)))
-        self._ctx = ctx
+        self._ctx_obj = None
+        if not getattr(self, '_lazy_ctx', False):
+            self._create_ctx()
         self._field_handles = {n: DeviceField(self, n) for n in _FIELDS}
         self._dirty = True
         self._malloc_called = False
@@ -251,20 +248,39 @@ class Basic3D:
             self.MPIcomm.register(self, kwargs.get('group_key', 'space'))
         self.MPIcomm.Barrier()
 
+    def _create_ctx(self):
+        cfg = _lib.Config(self.myNx, self.Ny, self.Nz, _lib.DTYPE_CODE[np.dtype(self.field_dtype)],
+                          _lib.METHOD_CODE[self.method], self.MPIrank, self.MPIsize, int(self.device),
+                          self.dx, self.dy, self.dz, self.dt)
+        ctx = C.c_void_p()
+        _lib.check(self._lib.ies_create(C.byref(cfg), C.byref(ctx)))
+        self._ctx_obj = ctx
+
+    @property
+    def _ctx(self):
+        """The engine context; an Empty3D creates its own only if somebody asks for its fields before
+        get_SF made it a (TF, IF) view (a full six-field slab otherwise sits unused: 3 GiB at the
+        headline grid)."""
+        if self._ctx_obj is None:
+            self._create_ctx()
+        return self._ctx_obj
+
     Ex = _field_property('Ex'); Ey = _field_property('Ey'); Ez = _field_property('Ez')
     Hx = _field_property('Hx'); Hy = _field_property('Hy'); Hz = _field_property('Hz')
 
     def __del__(self):
         try:
-            if getattr(self, '_ctx', None) is not None and self._ctx.value:
-                self._lib.ies_destroy(self._ctx)
-                self._ctx = None
+            if getattr(self, '_ctx_obj', None) is not None and self._ctx_obj.value:
+                self._lib.ies_destroy(self._ctx_obj)
+                self._ctx_obj = None
         except Exception:
             pass
 
     def _use_stream(self, stream):
-        if getattr(self, '_stream', None) != stream:
-            _lib.check(self._lib.ies_set_stream(self._ctx, C.c_void_p(stream)))
+        """Run on an external CUDA stream handle (int; 0 = the caller's default stream), or on the
+        context's own stream again with stream=None."""
+        if getattr(self, '_stream', 'own') != stream:
+            _lib.check(self._lib.ies_set_stream(self._ctx, C.c_void_p(stream or 0), int(stream is None)))
             self._stream = stream
 
     def sync(self):
@@ -306,6 +322,18 @@ class Basic3D:
         self.mu_Hx = self.mu_Hy = self.mu_Hz = self.mu
         self._malloc_called = True
         self._dirty = True
+
+    _COND = ('econ_Ex', 'econ_Ey', 'econ_Ez', 'mcon_Hx', 'mcon_Hy', 'mcon_Hz')
+
+    def __getattr__(self, name):
+        # the reference's conductivity arrays (space.py:223-234) are identically zero in every shipped
+        # script and the engine drops the C1 coefficient on that ground: they exist only when a
+        # script touches them, and init_update_constants() refuses non-zero values
+        if name in Basic3D._COND and self.__dict__.get('_malloc_called'):
+            arr = np.zeros(self.loc_grid, dtype=np.float64)
+            self.__dict__[name] = arr
+            return arr
+        raise AttributeError(f"'{type(self).__name__}' object has no attribute '{name}'")
 
     # --------------------------------------------------------------- apply_PML
     def apply_PML(self, region, npml):
@@ -413,6 +441,10 @@ class Basic3D:
         C1 == 1 exactly and one f64 array per half-step is uploaded:
         CH2 = -2dt/(2mu), CE2 = 2dt/(2eps), evaluated with the reference's expression."""
         assert self._malloc_called, "call malloc() first"
+        for nm in Basic3D._COND:
+            if nm in self.__dict__ and np.any(self.__dict__[nm]):
+                raise NotImplementedError(f"{nm} != 0: the b200 engine implements the lossless update "
+                                          "(C1 == 1); conductive media are not supported")
         self.CHx2 = self.CHy2 = self.CHz2 = (-2 * self.dt) / (2. * self.mu)
         self.CEx2 = self.CEy2 = self.CEz2 = (2. * self.dt) / (2. * self.eps)
         n = self.CHx2.size
@@ -675,6 +707,7 @@ class Empty3D(Basic3D):
 
     def __init__(self, grid, gridgap, dt, tsteps, field_dtype, mmtdtype, **kwargs):
         self._pair = None
+        self._lazy_ctx = True           # no device fields until somebody needs them
         Basic3D.__init__(self, grid, gridgap, dt, tsteps, field_dtype, mmtdtype, **kwargs)
 
     def get_SF(self, TF, IF):

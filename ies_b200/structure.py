@@ -10,6 +10,11 @@ floating-point operations, so the rasters are identical cell for cell.
 import numpy as np
 from scipy.constants import c, mu_0, epsilon_0
 
+try:
+    from . import comm as _comm
+except ImportError:  # sys.path drop-in
+    import comm as _comm
+
 
 class Structure:
 
@@ -18,26 +23,8 @@ class Structure:
         self.space = space
 
     def _get_local_x_loc(self, gxsrts, gxends):
-        """structure.py:17-107 (same clipping as collector._get_local_x_loc)."""
-        assert gxsrts >= 0
-        assert gxends < self.space.Nx
-        bxsrt = self.space.myNx_indice[self.space.MPIrank][0]
-        bxend = self.space.myNx_indice[self.space.MPIrank][1]
-        gxloc = None
-        lxloc = None
-        if gxsrts >= bxsrt and gxsrts < bxend and gxends <= bxend:
-            gxloc = (gxsrts, gxends)
-            lxloc = (gxsrts - bxsrt, gxends - bxsrt)
-        if gxsrts >= bxsrt and gxsrts < bxend and gxends > bxend:
-            gxloc = (gxsrts, bxend)
-            lxloc = (gxsrts - bxsrt, bxend - bxsrt)
-        if gxsrts < bxsrt and gxends > bxend:
-            gxloc = (bxsrt, bxend)
-            lxloc = (bxsrt - bxsrt, bxend - bxsrt)
-        if gxsrts < bxsrt and gxends > bxsrt and gxends <= bxend:
-            gxloc = (bxsrt, gxends)
-            lxloc = (bxsrt - bxsrt, gxends - bxsrt)
-        return gxloc, lxloc
+        """structure.py:17-107: the one shared statement of the rule lives in comm.local_x_loc."""
+        return _comm.local_x_loc(self.space, gxsrts, gxends)
 
     def _fill(self, index, mask=None):
         sp = self.space

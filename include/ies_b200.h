@@ -69,9 +69,10 @@ int ies_device_count(int* n);
  * per-method scratch on cfg->device; fields start at zero. */
 int ies_create(const ies_config* cfg, ies_ctx** out);
 int ies_destroy(ies_ctx* ctx);
-/* Use an externally owned stream (e.g. torch's current stream, for NCCL ordering).
- * stream = 0 restores the context's own stream. */
-int ies_set_stream(ies_ctx* ctx, void* cuda_stream);
+/* Run the context's work on an externally owned stream (use_own_stream = 0; a handle of 0 is then
+ * the caller's legacy default stream, not a special value) or go back to the context's own
+ * non-blocking stream (use_own_stream = 1, cuda_stream ignored). */
+int ies_set_stream(ies_ctx* ctx, void* cuda_stream, int use_own_stream);
 int ies_sync(ies_ctx* ctx);
 /* Engine tuning knobs (no reference counterpart; defaults need no call).  Names:
  * "fused" (SHPF, real dtypes, ny == nz in {64,128,256,512}: 1 = the half-step as one launch,

@@ -50,6 +50,7 @@ class _SingleComm:
     def Get_size(self): return 1
     def Barrier(self): pass
     def barrier(self): pass
+    def gather(self, obj, root=0): return [obj]
 
 
 class FakeWorld:
@@ -80,6 +81,21 @@ class FakeComm:
 
     def recv(self, source, tag=0):
         return self.world.box(source, self.rank, tag).get(timeout=120)
+
+
+class _Noop:
+    """Absorbs any attribute access / call / indexing: the plotting calls of the reference's scripts."""
+    def __getattr__(self, k): return _Noop()
+    def __call__(self, *a, **k): return _Noop()
+    def __getitem__(self, k): return _Noop()
+    def __iter__(self): return iter((_Noop(), _Noop()))
+
+
+class _NoopModule(types.ModuleType):
+    def __getattr__(self, k):
+        if k.startswith('__'):
+            raise AttributeError(k)
+        return _Noop()
 
 
 _tls = threading.local()
@@ -119,7 +135,7 @@ def _install_shims():
         try:
             importlib.import_module(name)
         except Exception:
-            mod = types.ModuleType(name)
+            mod = _NoopModule(name) if name != 'h5py' else types.ModuleType(name)
             mod.__path__ = []
             sys.modules[name] = mod
             if '.' in name:
@@ -144,15 +160,18 @@ def _patch_list_indices(src):
 _cache = {}
 
 
-def load_reference():
-    """Returns a namespace with the reference's space/source/collector/structure modules."""
-    if 'ns' in _cache:
+def load_reference(extra=()):
+    """Returns a namespace with the reference's space/source/collector/structure modules
+    (+ `extra`, e.g. plotter / recorder for the script-level goldens)."""
+    if 'ns' in _cache and all(hasattr(_cache['ns'], n) for n in extra):
         return _cache['ns']
     if not reference_available():
         raise RuntimeError('the reference is not present on this machine (/root/reference or oracle/_ref)')
     _install_shims()
-    ns = types.SimpleNamespace()
-    for name in ('space', 'source', 'collector', 'structure'):
+    ns = _cache.get('ns') or types.SimpleNamespace()
+    for name in ('space', 'source', 'collector', 'structure') + tuple(extra):
+        if hasattr(ns, name):
+            continue
         path = os.path.join(REF, name + '.py')
         with open(path) as f:
             src = f.read()
@@ -160,7 +179,19 @@ def load_reference():
             src = _patch_list_indices(src)
         mod = types.ModuleType('ies_reference_' + name)
         mod.__file__ = path
-        exec(compile(src, path, 'exec'), mod.__dict__)
+        # the reference's modules import each other by their top-level names (recorder.py:2)
+        saved = {n: sys.modules.get(n) for n in ('space', 'source', 'collector', 'structure')}
+        for n in saved:
+            if hasattr(ns, n):
+                sys.modules[n] = getattr(ns, n)
+        try:
+            exec(compile(src, path, 'exec'), mod.__dict__)
+        finally:
+            for n, m in saved.items():
+                if m is None:
+                    sys.modules.pop(n, None)
+                else:
+                    sys.modules[n] = m
         setattr(ns, name, mod)
     _cache['ns'] = ns
     return ns
