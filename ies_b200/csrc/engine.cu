@@ -487,8 +487,16 @@ static int do_update(ies_ctx* c, int half, int phase) {
     UpdParams p;
     if (fill_params(c, half, p)) return 1;
     const int nx = c->cfg.nx, ny = c->cfg.ny, nz = c->cfg.nz;
-    const bool fused = c->cfg.method == IES_SHPF && c->use_fused && !CP && c->cfg.ny == c->cfg.nz &&
-                       (c->cfg.ny == 64 || c->cfg.ny == 128 || c->cfg.ny == 256 || c->cfg.ny == 512);
+    // use_fused: 1 = wherever instantiated, 0 = never, -1 (default) = where it was measured faster: lines
+    // up to 256 points (at 512 the z role's stage tables and padded exchange take 98 KB per CTA and
+    // leave 32 KB of L1 to the streaming phase: 4.58 vs 3.94 ms/step on 256x512x512)
+    const bool fused_ok = c->cfg.method == IES_SHPF && !CP && c->cfg.ny == c->cfg.nz &&
+                          (c->cfg.ny == 64 || c->cfg.ny == 128 || c->cfg.ny == 256 || c->cfg.ny == 512);
+    // ... and no CPML on the y / z faces (their terms sit in every y-line tile; with the psi lines
+    // prefetched into L2 the two-kernel path runs them faster: 3.87 vs 4.17 ms/step on 1024x256x256)
+    bool yz_pml = false;
+    for (int t = 0; t < p.nterms; ++t) yz_pml |= p.terms[t].axis != 0;
+    const bool fused = fused_ok && (c->use_fused > 0 || (c->use_fused < 0 && c->cfg.ny <= 256 && !yz_pml));
     const bool overlap_ok = c->cfg.method != IES_FDTD && !fused;
     if (!overlap_ok) { if (phase == 0) return 0; phase = -1; }       // everything in phase 1
     if (c->cfg.method == IES_FDTD) {
@@ -631,7 +639,7 @@ static int create_impl(const ies_config* cfg, ies_ctx* c) {
     if (const char* e = getenv("IES_B200_PALETTE")) c->use_palette = atoi(e);
     for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
     // spectral scratch is allocated on first use
-    c->use_fused = 1; c->fused_lead = 3; c->fused_ring_planes = 0; c->fused_ring_alloc = 0;
+    c->use_fused = -1; c->fused_lead = 3; c->fused_ring_planes = 0; c->fused_ring_alloc = 0;
     c->fused_ring[0] = c->fused_ring[1] = nullptr; c->fused_sync = nullptr; c->twz_t = nullptr; c->fused_prof = nullptr; c->fused_prof_mem = nullptr;
     if (const char* e = getenv("IES_B200_FUSED")) c->use_fused = atoi(e);
     if (const char* e = getenv("IES_B200_FUSED_LEAD")) c->fused_lead = std::max(1, atoi(e));

@@ -179,6 +179,7 @@ k_shpf_fused(const UpdParams p, const FusedParams fp,
         const int i = p.i0 + py;
         const int kb = r - fp.zt;
         long long t0 = fp.prof ? clock64() : 0;
+        if (p.nterms) prefetch_tile_psi<T, CPLX>(p, i, kb * YCfg<T, CPLX, NY>::W, min((kb + 1) * YCfg<T, CPLX, NY>::W, p.nz));
         const C* twy_ = twy;
         const C* mly_ = mly;
         if constexpr (YM == 1) {

@@ -360,6 +360,7 @@ __device__ __forceinline__ void yline_phase_b_dispatch(const UpdParams& p, const
     const bool fast = mask == 0u && upd >= 0;
     if (fast && cuni == cuni) yline_phase_b<T, CPLX, N, 2, true>(p, i, k0, mask, upd, xbuf, cuni, dz_off);
     else if (fast) yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), true>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
+    else if (cuni == cuni) yline_phase_b<T, CPLX, N, 2, false>(p, i, k0, mask, upd, xbuf, cuni, dz_off);   // CPML tile, one coefficient
     else yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), false>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
 }
 
@@ -371,6 +372,8 @@ k_yline_update(const UpdParams p, const typename Cx<T>::type* __restrict__ tw,
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* xbuf = reinterpret_cast<C*>(smem_raw);      // NF buffers of N*W: exchange, then derivative stash
     const int i = p.i0 + (int)blockIdx.y;
+    if (p.nterms) prefetch_tile_psi<T, CPLX>(p, i, (int)blockIdx.x * YCfg<T, CPLX, N>::W,
+                                             min(((int)blockIdx.x + 1) * YCfg<T, CPLX, N>::W, p.nz));
     yline_phase_a<T, CPLX, N>(p, i, (int)blockIdx.x * YCfg<T, CPLX, N>::W, xbuf, tw, ml);
     __syncthreads();
     yline_phase_b_dispatch<T, CPLX, N, PAL>(p, i, (int)blockIdx.x, (int)gridDim.x, xbuf, p.dz_off);

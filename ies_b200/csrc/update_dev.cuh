@@ -198,6 +198,34 @@ __device__ __forceinline__ void cell_update_regs(const UpdParams& p, unsigned ma
     }
 }
 
+// L2 prefetch of the CPML auxiliary fields a y-line tile (plane i, columns [k0, k1), all rows) is
+// going to touch.  The term walk of cell_update_regs loads psi inside a data-dependent loop, one
+// dependent round trip per term; under load a round trip to HBM costs ~2.8 us (15 MB in flight at
+// 5.6 TB/s), an L2 hit a fraction of it.  Issued at the start of the tile's work (before its FFT
+// phase, ~10 us ahead of the use), costs no registers and nothing to wait for; the psi lines of a
+// tile are a few KB (unlike the tile's field operands, whose prefetch thrashes L2).
+template <typename T, bool CPLX>
+__device__ __forceinline__ void prefetch_tile_psi(const UpdParams& p, int i, int k0, int k1) {
+    constexpr int ES = (int)sizeof(T) * (CPLX ? 2 : 1);
+    for (int t = 0; t < p.nterms; ++t) {
+        const PmlTermDev& q = p.terms[t];
+        if (i < q.lo[0] || i >= q.hi[0]) continue;
+        const int ka = max(k0, q.lo[2]), kb = min(k1, q.hi[2]) - 1;
+        if (ka > kb) continue;
+        for (int j = q.lo[1] + (int)threadIdx.x; j < q.hi[1]; j += (int)blockDim.x) {
+            const int ax = q.axis;
+            const int na = (ax == 0 ? i - q.lo[0] : ax == 1 ? j - q.lo[1] : ka - q.lo[2]) + q.psi_off;
+            const int nb = (ax == 0 ? i - q.lo[0] : ax == 1 ? j - q.lo[1] : kb - q.lo[2]) + q.psi_off;
+            const size_t ia = ((size_t)(ax == 0 ? na : i) * q.pdim[1] + (ax == 1 ? na : j)) * q.pdim[2] + (ax == 2 ? na : ka);
+            const size_t ib = ((size_t)(ax == 0 ? nb : i) * q.pdim[1] + (ax == 1 ? nb : j)) * q.pdim[2] + (ax == 2 ? nb : kb);
+            const char* pa = (const char*)q.psi + ia * ES;
+            const char* pb = (const char*)q.psi + ib * ES;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pa));
+            if (((size_t)pa >> 7) != ((size_t)pb >> 7)) asm volatile("prefetch.global.L2 [%0];" ::"l"(pb));
+        }
+    }
+}
+
 // Tile-level classification against the three update boxes: returns the bit mask of the
 // components whose box contains the whole tile [i0,i1) x [j0,j1) x [k0,k1) when every box
 // either contains the tile or misses it completely, else -1 (per-cell tests needed).

@@ -77,7 +77,7 @@ int ies_sync(ies_ctx* ctx);
 /* Engine tuning knobs (no reference counterpart; defaults need no call).  Names:
  * "fused" (SHPF, real dtypes, ny == nz in {64,128,256,512}: 1 = the half-step as one launch,
  * z-line and y-line tiles as two roles of one grid [shpf_fused.cuh]; 0 = z-line derivative kernel +
- * y-line update kernel), "fused_lead" (planes the z role runs ahead), "fused_ring" (scratch ring
+ * y-line update kernel; -1 [default] = fused for lines up to 256 points, where it is faster), "fused_lead" (planes the z role runs ahead), "fused_ring" (scratch ring
  * size in planes, 0 = full-size scratch), "palette" (1 = palette-compressed coefficient arrays
  * when they hold <= 32 distinct values; default 0), "reset_psi" (zero the CPML auxiliary
  * arrays). */

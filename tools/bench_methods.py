@@ -15,6 +15,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+import bench  # noqa: E402  (ClockSampler, measured_peak)
 um = 1e-6
 C0 = 299792458.0
 
@@ -40,7 +41,7 @@ BYTES = {np.float64: 160, np.float32: 88, np.complex64: 160, np.complex128: 304}
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--only', type=int, default=-1, help='index into CASES')
     ap.add_argument('--grep', default='', help='only cases whose label/grid string contains this')
@@ -48,6 +49,7 @@ def main():
     import ies_b200
     from ies_b200 import _lib
     lib = _lib.load()
+    peak, _ = bench.measured_peak()
     rows = []
     for method, dt_, grid in (CASES if args.only < 0 else CASES[args.only:args.only + 1]):
         if args.grep and args.grep not in f'{method} {np.dtype(dt_).name} {grid}': continue
@@ -82,21 +84,26 @@ def main():
             sp.updateH(t); sp.updateE(t)
         for t in range(args.warmup): step(t)
         sp.sync()
+        clk = bench.ClockSampler(0)
+        clk.start()
         _lib.check(lib.ies_timer_start(sp._ctx))
         for t in range(args.steps): step(t)
         ms = C.c_double()
         _lib.check(lib.ies_timer_stop(sp._ctx, C.byref(ms)))
+        clocks = clk.stop()
         per = ms.value / args.steps
         ncell = nx * ny * nz
         g = ncell / per / 1e6
         finite = bool(np.all(np.isfinite(np.asarray(sp.Ey[nx // 2, :4, :4]))))
         row = dict(method=label, dtype=np.dtype(dt_).name, grid=list(grid), ms_per_step=round(per, 4), gcell_s=round(g, 2),
-                   gbs_algorithmic=round(g * BYTES[dt_], 0), finite=finite)
+                   gbs_algorithmic=round(g * BYTES[dt_], 0), frac_of_hbm_peak=round(g * BYTES[dt_] / peak, 3),
+                   finite=finite, steps=args.steps, clocks=clocks)
         rows.append(row)
         print(json.dumps(row), flush=True)
         del sp, setter
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-    json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'methods.json'), 'w'), indent=1)
+    if args.only < 0 and not args.grep:
+        json.dump(rows, open(os.path.join(ROOT, 'gpurun_out', 'methods.json'), 'w'), indent=1)
 
 
 if __name__ == '__main__':

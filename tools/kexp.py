@@ -31,7 +31,7 @@ VARIANTS = [
     ('palette', dict(fused=0, palette=1, ctile=0)),
 ]
 ALL_OPTS = ('fused', 'fused_ring', 'fused_lead', 'palette', 'ctile')
-DEFAULTS = dict(fused=1, fused_ring=0, fused_lead=3, palette=0, ctile=1)
+DEFAULTS = dict(fused=-1, fused_ring=0, fused_lead=3, palette=0, ctile=1)
 
 
 def main():

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep (read here, no GPU needed) into the JSON kept under profiles/.
 
-    python tools/ncu_summary.py gpurun_out/prof_yline_r1.ncu-rep [more.ncu-rep ...] > profiles/ncu_summary.json
+    python tools/ncu_summary.py gpurun_out/prof_fused.ncu-rep gpurun_out/prof_mie_y.ncu-rep:_mie ... > profiles/ncu_summary.json
 """
 import csv
 import io
@@ -81,11 +81,15 @@ def summarise(path):
 
 
 if __name__ == '__main__':
+    # arguments: report.ncu-rep[:suffix]  -- the suffix names the workload ("_mie", "_c128" ...)
     allk = {}
-    for p in sys.argv[1:]:
+    for arg in sys.argv[1:]:
+        p, _, suffix = arg.partition(':')
         for e in summarise(p):
             key = 'k_yline_update' if 'k_yline_update' in e['kernel'] else 'k_zline' if 'k_zline' in e['kernel'] \
-                else 'k_shpf_fused' if 'fused' in e['kernel'] else 'k_fdtd' if 'k_fdtd' in e['kernel'] else e['kernel'][:40]
+                else 'k_shpf_fused' if 'fused' in e['kernel'] else 'k_fdtd' if 'k_fdtd' in e['kernel'] \
+                else 'k_xline' if 'k_xline' in e['kernel'] else e['kernel'][:40]
+            key += suffix
             allk.setdefault(key, e)
             allk[key]['source_report'] = p
     json.dump(allk, sys.stdout, indent=1, sort_keys=True)
