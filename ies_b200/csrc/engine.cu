@@ -496,7 +496,9 @@ static int do_update(ies_ctx* c, int half, int phase) {
     // prefetched into L2 the two-kernel path runs them faster: 3.87 vs 4.17 ms/step on 1024x256x256)
     bool yz_pml = false;
     for (int t = 0; t < p.nterms; ++t) yz_pml |= p.terms[t].axis != 0;
-    const bool fused = fused_ok && (c->use_fused > 0 || (c->use_fused < 0 && c->cfg.ny <= 256 && !yz_pml));
+    // ... and double precision (fp32: 2.32 vs 2.09 ms/step on 1024x256x256 -- half the bytes per tile, the
+    // roles' fixed costs weigh twice as much)
+    const bool fused = fused_ok && (c->use_fused > 0 || (c->use_fused < 0 && c->cfg.ny <= 256 && !yz_pml && c->dbl));
     const bool overlap_ok = c->cfg.method != IES_FDTD && !fused;
     if (!overlap_ok) { if (phase == 0) return 0; phase = -1; }       // everything in phase 1
     if (c->cfg.method == IES_FDTD) {
@@ -603,7 +605,7 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     IES_CUDA(cudaSetDevice(cfg->device));
     ies_ctx* c = new ies_ctx();
     c->own_stream = nullptr; c->ev_halo = nullptr; c->ev_t0 = c->ev_t1 = nullptr;
-    c->stage = nullptr; c->stage_bytes = 0; c->seq_ring = nullptr;
+    c->stage = nullptr; c->stage_bytes = 0; c->seq_ring = nullptr; c->src_tab = nullptr; c->src_tab_bytes = 0;
     c->peer_block[0] = c->peer_block[1] = nullptr;
     if (create_impl(cfg, c)) {              // the error text survives the clean-up
         const std::string keep = ies_last_error();
@@ -639,7 +641,7 @@ static int create_impl(const ies_config* cfg, ies_ctx* c) {
     if (const char* e = getenv("IES_B200_PALETTE")) c->use_palette = atoi(e);
     for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
     // spectral scratch is allocated on first use
-    c->use_fused = -1; c->fused_lead = 3; c->fused_ring_planes = 0; c->fused_ring_alloc = 0;
+    c->use_fused = -1; c->fused_zb = 2; c->fused_prefetch = 0; c->fused_lead = 6; c->fused_ring_planes = 0; c->fused_ring_alloc = 0;
     c->fused_ring[0] = c->fused_ring[1] = nullptr; c->fused_sync = nullptr; c->twz_t = nullptr; c->fused_prof = nullptr; c->fused_prof_mem = nullptr;
     if (const char* e = getenv("IES_B200_FUSED")) c->use_fused = atoi(e);
     if (const char* e = getenv("IES_B200_FUSED_LEAD")) c->fused_lead = std::max(1, atoi(e));
@@ -680,30 +682,36 @@ static int create_impl(const ies_config* cfg, ies_ctx* c) {
         IES_CUDA(cudaStreamSynchronize(c->stream));
     }
     if (cfg->method == IES_SHPF) {
-        // fused half-step: counters, and the z axis' stage tables transposed to [m][jj]
-        // (fft_dev.cuh TwTables: forward stage NS = 16, inverse stage NS = N/16; one table at N = 256)
-        { void* q; if (dev_alloc(c, &q, sizeof(unsigned) * (size_t)(1 + 2 * cfg->nx))) return 1; c->fused_sync = (unsigned*)q; }
-        const int n = cfg->nz;
-        if (n > 16) {
-            const int r1 = (n / 16 >= 16) ? 16 : n / 16, fwd = r1 * 16, nsi = n / 16, fstep = n / (16 * r1);
-            const bool shared = n == 256;
-            const int tot = (shared ? 0 : fwd) + n;
-            std::vector<double> hd(2 * (size_t)tot);
-            std::vector<float> hf(2 * (size_t)tot);
-            auto W = [&](int k, int at) {
-                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)(k & (n - 1)) / (long double)n;
-                hd[2 * at] = (double)cosl(ang); hd[2 * at + 1] = (double)sinl(ang);
-                hf[2 * at] = (float)hd[2 * at]; hf[2 * at + 1] = (float)hd[2 * at + 1];
-            };
-            int at = 0;
-            if (!shared) for (int q = 0; q < fwd; ++q) W((q / 16) * (q % 16) * fstep, at++);
-            for (int q = 0; q < n; ++q) W((q / nsi) * (q % nsi), at++);
-            const size_t b = (size_t)2 * tot * (c->dbl ? 8 : 4);
-            if (dev_alloc(c, &c->twz_t, b, false)) return 1;
-            IES_CUDA(cudaMemcpyAsync(c->twz_t, c->dbl ? (void*)hd.data() : (void*)hf.data(), b, cudaMemcpyHostToDevice, c->stream));
-            IES_CUDA(cudaStreamSynchronize(c->stream));
-        }
+        // fused half-step: ticket + per-plane counters
+        void* q; if (dev_alloc(c, &q, sizeof(unsigned) * (size_t)(1 + 2 * cfg->nx))) return 1; c->fused_sync = (unsigned*)q;
     }
+    // stage tables of the y and z axes transposed to [m][jj] (fft_dev.cuh TwTables: forward stage NS = 16,
+    // inverse stage NS = N/16; one table at N = 256): lines handled by adjacent lanes read them coalesced
+    for (int a = 1; a < 3; ++a) {
+        c->tw_t[a] = nullptr;
+        if (cfg->method == IES_FDTD) continue;
+        const int n = dims[a];
+        if (n <= 16) continue;
+        const int r1 = (n / 16 >= 16) ? 16 : n / 16, fwd = r1 * 16, nsi = n / 16, fstep = n / (16 * r1);
+        const bool shared = n == 256;
+        const int tot = (shared ? 0 : fwd) + n;
+        std::vector<double> hd(2 * (size_t)tot);
+        std::vector<float> hf(2 * (size_t)tot);
+        auto W = [&](int k, int at) {
+            const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)(k & (n - 1)) / (long double)n;
+            hd[2 * at] = (double)cosl(ang); hd[2 * at + 1] = (double)sinl(ang);
+            hf[2 * at] = (float)hd[2 * at]; hf[2 * at + 1] = (float)hd[2 * at + 1];
+        };
+        int at = 0;
+        if (!shared) for (int q = 0; q < fwd; ++q) W((q / 16) * (q % 16) * fstep, at++);
+        for (int q = 0; q < n; ++q) W((q / nsi) * (q % nsi), at++);
+        const size_t b = (size_t)2 * tot * (c->dbl ? 8 : 4);
+        if (dev_alloc(c, &c->tw_t[a], b, false)) return 1;
+        IES_CUDA(cudaMemcpyAsync(c->tw_t[a], c->dbl ? (void*)hd.data() : (void*)hf.data(), b, cudaMemcpyHostToDevice, c->stream));
+        IES_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    c->tw_t[0] = nullptr;
+    c->twz_t = c->tw_t[2];
     for (int q = 0; q < 6; ++q) {
         c->ubox[q].lo[0] = c->ubox[q].lo[1] = c->ubox[q].lo[2] = 0;
         c->ubox[q].hi[0] = cfg->nx; c->ubox[q].hi[1] = cfg->ny; c->ubox[q].hi[2] = cfg->nz;
@@ -721,6 +729,7 @@ int ies_destroy(ies_ctx* c) {
     cudaStreamSynchronize(c->stream);
     for (void* p : c->owned) cudaFree(p);
     if (c->stage) cudaFree(c->stage);
+    if (c->src_tab) cudaFree(c->src_tab);
     for (int n = 0; n < 2; ++n) if (c->peer_block[n]) cudaIpcCloseMemHandle(c->peer_block[n]);
     if (c->seq_ring) cudaFreeHost(c->seq_ring);
     if (c->ev_halo) cudaEventDestroy(c->ev_halo);
@@ -742,6 +751,8 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     else if (n == "fdtd_vec") c->fdtd_vec = v;
     else if (n == "fused") c->use_fused = v;
     else if (n == "fused_lead") c->fused_lead = v < 1 ? 1 : v;
+    else if (n == "fused_zb") c->fused_zb = v == 2 ? 2 : 1;
+    else if (n == "fused_prefetch") c->fused_prefetch = v;
     else if (n == "fused_ring") c->fused_ring_planes = v;
     else if (n == "fused_prof") {               // 1: start (zeroed) per-phase cycle counters, 0: stop
         if (v && !c->fused_prof_mem) { void* q; if (dev_alloc(c, &q, 16 * 8)) return 1; c->fused_prof_mem = (unsigned long long*)q; }
@@ -825,7 +836,10 @@ int ies_set_coeff(ies_ctx* c, int half, const double* host, int64_t n) {
     if (c->cfg.method != IES_FDTD) {
         // per-tile uniform coefficients for the y-line kernel (tile = 4096/ny columns of one plane)
         // = YCfg::W of spectral.cuh: 256 threads (128 for complex dtypes, lines up to 1024) / (ny/16)
-        const int thr = (c->cplx && c->cfg.ny / 16 <= 64) ? 128 : 256;
+#ifndef IES_Y512_THREADS
+#define IES_Y512_THREADS 256
+#endif
+        const int thr = (c->cplx && c->cfg.ny / 16 <= 64) ? 128 : ((!c->cplx && c->cfg.ny == 512) ? IES_Y512_THREADS : 256);
         const int w = thr * 16 / c->cfg.ny > 0 ? thr * 16 / c->cfg.ny : 1;
         const int kt = (c->cfg.nz + w - 1) / w;
         if (!c->Ctile[half]) { void* p; if (dev_alloc(c, &p, (size_t)c->cfg.nx * kt * 8, false)) return 1; c->Ctile[half] = (double*)p; }
@@ -1097,21 +1111,35 @@ int ies_put_src(ies_ctx* c, int comp, const int32_t lo[3], const int32_t hi[3], 
     if (n <= 0) return 0;
     IES_CUDA(cudaSetDevice(c->cfg.device));
     double2 *dpx = nullptr, *dpy = nullptr, *dpz = nullptr;
-    void* tmp = nullptr;
     if (px && py && pz) {
         if (!c->cplx) { set_error("Bloch phase tables need a complex field dtype"); return 1; }
+        // The phase tables of a Setter never change between calls: they live in a per-context device
+        // buffer with a host shadow, and are uploaded only when their content differs (a per-call
+        // cudaMallocAsync + three pageable H2D copies put a stream synchronisation and milliseconds of
+        // host time into every step of the Bloch-boundary runs).
         const int ex = hi[0] - lo[0], ey = hi[1] - lo[1], ez = hi[2] - lo[2];
-        IES_CUDA(cudaMallocAsync(&tmp, (size_t)(ex + ey + ez) * 16, c->stream));
-        dpx = (double2*)tmp; dpy = dpx + ex; dpz = dpy + ey;
-        IES_CUDA(cudaMemcpyAsync(dpx, px, (size_t)ex * 16, cudaMemcpyHostToDevice, c->stream));
-        IES_CUDA(cudaMemcpyAsync(dpy, py, (size_t)ey * 16, cudaMemcpyHostToDevice, c->stream));
-        IES_CUDA(cudaMemcpyAsync(dpz, pz, (size_t)ez * 16, cudaMemcpyHostToDevice, c->stream));
+        const size_t cnt = (size_t)(ex + ey + ez) * 2;
+        std::vector<double> want(cnt);
+        memcpy(want.data(), px, (size_t)ex * 16);
+        memcpy(want.data() + 2 * ex, py, (size_t)ey * 16);
+        memcpy(want.data() + 2 * (ex + ey), pz, (size_t)ez * 16);
+        if (c->src_tab_bytes < cnt * 8) {
+            if (c->src_tab) { IES_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(c->src_tab); c->src_tab = nullptr; }
+            IES_CUDA(cudaMalloc(&c->src_tab, cnt * 8));
+            c->src_tab_bytes = cnt * 8;
+            c->src_tab_host.clear();
+        }
+        if (c->src_tab_host != want) {
+            IES_CUDA(cudaStreamSynchronize(c->stream));      // a queued injection may still read the old tables
+            IES_CUDA(cudaMemcpy(c->src_tab, want.data(), cnt * 8, cudaMemcpyHostToDevice));
+            c->src_tab_host.swap(want);
+        }
+        dpx = (double2*)c->src_tab; dpy = dpx + ex; dpz = dpy + ey;
     }
     DISPATCH(c, k_put_src<T, CP><<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(
         c->F[comp], c->cfg.ny, c->cfg.nz, bx, make_double2(re, im), hard, dpx, dpy, dpz));
     count_launch();
     IES_CUDA(cudaGetLastError());
-    if (tmp) IES_CUDA(cudaFreeAsync(tmp, c->stream));
     return 0;
 }
 

@@ -77,6 +77,7 @@ struct Ctx {
     int flag_write_mode;        // 0 = cuStreamWriteValue32, 1 = cudaMemcpyAsync from seq_ring
     void* mult[2][3];           // [half][axis] complex table in FFT precision, pre-scaled by 1/N
     void* tw[3];                // W_N master twiddles per axis
+    void* tw_t[3];              // stage tables transposed to [m][jj], [forward | inverse] (fft_dev.cuh TwTables)
     Box ubox[6];
     std::vector<PmlTermDev> terms[2];
     std::vector<void*> owned;   // device allocations freed at destroy
@@ -84,12 +85,16 @@ struct Ctx {
     double ghost_pp[3][2], ghost_pm[3][2];
     int has_prev, has_next;
     void* stage; size_t stage_bytes;   // staging buffer for get/set
+    void* src_tab; size_t src_tab_bytes;          // Setter phase tables px|py|pz (ies_put_src), device copy
+    std::vector<double> src_tab_host;             //   and the host shadow it was uploaded from
     cudaEvent_t ev_halo;
     cudaEvent_t ev_t0, ev_t1;          // ies_timer_start/stop
     int profiling;                     // per-kernel CUDA-event timing on/off
     std::vector<cudaEvent_t> prof_ev[4][2];   // [slot][begin/end]
     // fused single-launch SHPF half-step (shpf_fused.cuh)
     int use_fused;                     // 1 = k_shpf_fused where instantiated, 0 = k_zline + k_yline_update
+    int fused_prefetch;                // z role prefetches F_z and G of its rows into L2 for the y role
+    int fused_zb;                      // z tiles per z-role CTA (1 or 2)
     int fused_lead, fused_ring_planes; // planes of lead of the z role; scratch ring size in planes
     unsigned* fused_sync;              // ticket + zdone[nx] + ydone[nx]
     void* fused_ring[2];               // ring scratch (fused_ring_planes planes each) or null

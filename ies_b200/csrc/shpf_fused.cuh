@@ -34,6 +34,7 @@ struct FusedParams {
     int lead;                   // planes the z role runs ahead of the y role
     int ring;                   // scratch planes (ring > lead; ring >= nx: no wrap)
     int zt, yt;                 // tiles per plane of each role
+    int prefetch;               // z role prefetches the y role's streaming operands of its rows into L2
     unsigned long long* prof;   // null, or 16 counters of SM cycles per role phase (development: option fused_prof)
 };
 
@@ -77,8 +78,11 @@ template <int N, int ZM> struct FusedZSmem {
     static constexpr int ELEMS = TABLES + ZCfg<N, 16>::LPB * LS;      // complex elements
 };
 
-template <typename T, bool CPLX, int N, int ZM, bool SIGNAL = true>
-__device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedParams& fp, const int pz, const int tile,
+// ZB: z tiles per CTA, done one after the other with the tables staged once and ONE signal at the
+// end -- the release fence in front of the signal holds the CTA's slot until its stores are
+// acknowledged (2.9 k cycles per tile when every tile signals for itself).
+template <typename T, bool CPLX, int N, int ZM, int ZB>
+__device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedParams& fp, const int pz, const int tile0,
                                              typename Cx<T>::type* smem,
                                              const typename Cx<T>::type* __restrict__ tw,
                                              const typename Cx<T>::type* __restrict__ twt,
@@ -110,12 +114,28 @@ __device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedPara
         tw = s_tw; twf = s_twf; twi = s_twi; ml = s_ml;
     }
     const int t = threadIdx.x % TT, l = threadIdx.x / TT;
-    const int row = tile * LPB + l;
+    X xb{xbuf + (size_t)l * X::LS};
+    long long t0 = fp.prof ? clock64() : 0;
+    // Experiment (option fused_prefetch, off): the z role asks L2 for the rows of F_z and the three G
+    // arrays its plane's y tiles will stream `lead` planes later.  Measured: y update phase 17.7 k ->
+    // 18.8 k cycles, 3.07 -> 3.22 ms/step -- the update phase is not waiting for HBM latency (it is
+    // paced by the L1/LSU wavefront rate of its 16-byte row-segment accesses), so L2 hits do not help.
+    if (fp.prefetch) {
+        constexpr int ES = (int)sizeof(T) * (CPLX ? 2 : 1);
+        const size_t rows0 = ((size_t)pz * p.ny + (size_t)tile0 * LPB) * N * ES;
+        const int bytes = min(ZB * LPB, p.ny - tile0 * LPB) * N * ES;
+        const char* arr[4] = {(const char*)p.F[2], (const char*)p.G[0], (const char*)p.G[1], (const char*)p.G[2]};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            for (int off = (int)threadIdx.x * 128; off < bytes; off += (int)blockDim.x * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(arr[a] + rows0 + off));
+    }
+#pragma unroll 1
+    for (int zb = 0; zb < ZB; ++zb) {
+    const int row = (tile0 + zb) * LPB + l;
     const bool ok = row < p.ny;
     const size_t ibase = ((size_t)pz * p.ny + row) * N;
     const size_t obase = ((size_t)(pz % fp.ring) * p.ny + row) * N;
-    X xb{xbuf + (size_t)l * X::LS};
-    long long t0 = fp.prof ? clock64() : 0;
     C v[F::NF][16];
 #pragma unroll
     for (int f = 0; f < F::NF; ++f) {
@@ -142,14 +162,16 @@ __device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedPara
             for (int q = 0; q < 16; ++q) F::st(dA, dB, obase + line_index_v<N, 16>(t, q), v[f][q], f);
         }
     }
-    if (SIGNAL) signal_counter(fp.zdone + pz);
+    if (zb + 1 < ZB) { xb.sync(); continue; }       // the exchange buffer is re-used by the next tile
+    signal_counter(fp.zdone + pz);
     fprof(fp, 2, &t0);
-    if (fp.prof && threadIdx.x == 0) atomicAdd(fp.prof + 8, 1ull);
+    if (fp.prof && threadIdx.x == 0) atomicAdd(fp.prof + 8, (unsigned long long)ZB);
+    }
 }
 
 // YM = 0: the y role reads its twiddle / multiplier tables from global memory (L1), like
 // k_yline_update; YM = 1: it copies them behind the stash in shared memory first (+2N entries).
-template <typename T, bool CPLX, int NY, int NZ, int ZM, int YM>
+template <typename T, bool CPLX, int NY, int NZ, int ZM, int YM, int ZB>
 __global__ void __launch_bounds__(256, 2)
 k_shpf_fused(const UpdParams p, const FusedParams fp,
              const typename Cx<T>::type* __restrict__ twy, const typename Cx<T>::type* __restrict__ mly,
@@ -167,31 +189,28 @@ k_shpf_fused(const UpdParams p, const FusedParams fp,
     // y FFT 16.2 k instead of 12.6 k).
     if (threadIdx.x == 0) s_ticket = atomicAdd(fp.ticket, 1u);
     __syncthreads();
-    const int per = fp.zt + fp.yt;
+    const int zc = fp.zt / ZB;                      // z CTAs per plane (the launcher picks ZB | zt)
+    const int per = zc + fp.yt;
     const int g = (int)(s_ticket / (unsigned)per), r = (int)(s_ticket % (unsigned)per);
     const int nplanes = p.i1 - p.i0;
-    if (r < fp.zt) {
+    if (r < zc) {
         if (g >= nplanes) return;
-        fused_z_role<T, CPLX, NZ, ZM>(p, fp, p.i0 + g, r, xbuf, twz, twzt, mlz);
+        fused_z_role<T, CPLX, NZ, ZM, ZB>(p, fp, p.i0 + g, r * ZB, xbuf, twz, twzt, mlz);
     } else {
         const int py = g - fp.lead;
         if (py < 0) return;
         const int i = p.i0 + py;
-        const int kb = r - fp.zt;
+        const int kb = r - zc;
         long long t0 = fp.prof ? clock64() : 0;
         if (p.nterms) prefetch_tile_psi<T, CPLX>(p, i, kb * YCfg<T, CPLX, NY>::W, min((kb + 1) * YCfg<T, CPLX, NY>::W, p.nz));
-        const C* twy_ = twy;
-        const C* mly_ = mly;
-        if constexpr (YM == 1) {
-            C* s_tw = xbuf + (size_t)NY * YCfg<T, CPLX, NY>::W;
-            C* s_ml = s_tw + NY;
-            for (int q = threadIdx.x; q < NY; q += blockDim.x) { s_tw[q] = twy[q]; s_ml[q] = mly[q]; }
-            __syncthreads();
-            twy_ = s_tw; mly_ = s_ml;
-        }
-        yline_phase_a<T, CPLX, NY>(p, i, kb * YCfg<T, CPLX, NY>::W, xbuf, twy_, mly_);
+        // y tables (master W_N + multiplier) behind the stash; no barrier of their own: they are first
+        // read after the two barriers of the first exchange
+        C* s_tw = xbuf + (size_t)NY * YCfg<T, CPLX, NY>::W;
+        C* s_ml = s_tw + NY;
+        for (int q = threadIdx.x; q < NY; q += blockDim.x) { s_tw[q] = twy[q]; s_ml[q] = mly[q]; }
+        yline_phase_a<T, CPLX, NY>(p, i, kb * YCfg<T, CPLX, NY>::W, xbuf, s_tw, s_ml);
         fprof(fp, 3, &t0);
-        wait_counter(fp.zdone + i, (unsigned)fp.zt, fp.ring < p.i1 - p.i0);     // also the barrier that publishes the stash
+        wait_counter(fp.zdone + i, (unsigned)zc, fp.ring < p.i1 - p.i0);     // also the barrier that publishes the stash
         fprof(fp, 4, &t0);
         const long long plane = (long long)p.ny * p.nz;
         const long long dz_off = ((long long)(i % fp.ring) - (long long)i) * plane;
@@ -219,6 +238,7 @@ int launch_shpf_fused(Ctx* c, const UpdParams& p, int half) {
         fp.lead = c->fused_lead;
         fp.ring = c->fused_ring_planes;
         fp.prof = c->fused_prof;
+        fp.prefetch = c->fused_prefetch;
         IES_CUDA(cudaMemsetAsync(c->fused_sync, 0, sizeof(unsigned) * (size_t)(1 + 2 * c->cfg.nx), c->stream));
         const int nplanes = p.i1 - p.i0;
 #define F_CASE(NN) {                                                                        \
@@ -226,9 +246,10 @@ int launch_shpf_fused(Ctx* c, const UpdParams& p, int half) {
             fp.yt = (nz + YCfg<T, CPLX, NN>::W - 1) / YCfg<T, CPLX, NN>::W;                  \
             const size_t sm0 = sizeof(C) * (size_t)NN * YCfg<T, CPLX, NN>::W;                \
             const size_t sm = std::max(sizeof(C) * (size_t)FusedZSmem<NN, 1>::ELEMS, sm0 + sizeof(C) * 2 * NN); \
-            auto kern = k_shpf_fused<T, CPLX, NN, NN, 1, 1>;                                \
+            const bool z2 = c->fused_zb == 2 && fp.zt % 2 == 0;                            \
+            auto kern = z2 ? k_shpf_fused<T, CPLX, NN, NN, 1, 1, 2> : k_shpf_fused<T, CPLX, NN, NN, 1, 1, 1>; \
             if (set_smem(kern, sm)) return 1;                                               \
-            const unsigned grid = (unsigned)((nplanes + fp.lead) * (fp.zt + fp.yt));        \
+            const unsigned grid = (unsigned)((nplanes + fp.lead) * (fp.zt / (z2 ? 2 : 1) + fp.yt)); \
             kern<<<grid, 256, sm, c->stream>>>(p, fp, (const C*)c->tw[1], (const C*)c->mult[half][1], \
                 (const C*)c->tw[2], (const C*)c->twz_t, (const C*)c->mult[half][2]);        \
         }

@@ -139,9 +139,12 @@ template <typename T, bool CPLX, int N> struct SCfg {
 template <typename T, bool CPLX, int N> struct YCfg {
     static constexpr int TT = N / 16;
     static constexpr int ES = (int)sizeof(T) * (CPLX ? 2 : 1);
-    static constexpr int THREADS = (CPLX && TT <= 64) ? 128 : 256;
+#ifndef IES_Y512_THREADS
+#define IES_Y512_THREADS 256
+#endif
+    static constexpr int THREADS = (CPLX && TT <= 64) ? 128 : ((!CPLX && N == 512) ? IES_Y512_THREADS : 256);
     static constexpr int W = THREADS / TT;
-    static constexpr int MINB = CPLX ? 3 : 2;   // (real dtypes: 128-thread CTAs 1.14 -> 1.32 ms at N = 256; 512-thread CTAs at N = 512 +-3 %)   // (128-thread CTAs for real dtypes: 64-byte row segments, 1.14 -> 1.32 ms)                     // CTAs per SM the kernel is compiled for
+    static constexpr int MINB = CPLX ? 3 : (THREADS > 256 ? 1 : 2);   // (real dtypes: 128-thread CTAs 1.14 -> 1.32 ms at N = 256; 512-thread CTAs at N = 512 +-3 %)   // (128-thread CTAs for real dtypes: 64-byte row segments, 1.14 -> 1.32 ms)                     // CTAs per SM the kernel is compiled for
     static_assert(W >= 1 && W * ES >= 32, "row segment below one sector");
 };
 

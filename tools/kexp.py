@@ -23,15 +23,18 @@ import bench  # noqa: E402
 
 VARIANTS = [
     ('base', dict(fused=0)),                            # two-kernel path (k_zline + k_yline_update)
-    ('fused', dict(fused=1)),                           # single launch, full-size scratch, lead 3
-    ('fused_l1', dict(fused=1, fused_lead=1)),
-    ('fused_l6', dict(fused=1, fused_lead=6)),
+    ('fused', dict(fused=1)),                           # single launch, full-size scratch, defaults
+    ('fused_pf', dict(fused=1, fused_prefetch=1)),
+    ('fused_l3', dict(fused=1, fused_lead=3)),
+    ('fused_l10', dict(fused=1, fused_lead=10)),
+    ('fused_zb1', dict(fused=1, fused_zb=1)),
+    ('fused_zb1_l3', dict(fused=1, fused_zb=1, fused_lead=3)),
     ('fused_r32', dict(fused=1, fused_ring=32)),        # scratch ring of 32 planes
     ('noctile', dict(fused=0, ctile=0)),
     ('palette', dict(fused=0, palette=1, ctile=0)),
 ]
-ALL_OPTS = ('fused', 'fused_ring', 'fused_lead', 'palette', 'ctile')
-DEFAULTS = dict(fused=-1, fused_ring=0, fused_lead=3, palette=0, ctile=1)
+ALL_OPTS = ('fused', 'fused_ring', 'fused_lead', 'fused_zb', 'fused_prefetch', 'palette', 'ctile')
+DEFAULTS = dict(fused=-1, fused_ring=0, fused_lead=6, fused_zb=2, fused_prefetch=0, palette=0, ctile=1)
 
 
 def main():
