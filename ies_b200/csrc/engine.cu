@@ -7,6 +7,7 @@
 #include <atomic>
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "engine.h"
 #include "update_dev.cuh"
@@ -216,6 +217,102 @@ __global__ void k_put_src(void* f, int ny, int nz, Box bx, double2 pulse, int ha
     if constexpr (CPLX) add = make_double2(vr, vi); else add = vr;
     if (hard) E::st(f, idx, add);
     else E::st(f, idx, a_add(E::ld(f, idx), add));
+}
+
+// CPML corrections as a pass of their own over the absorber cells (space.py:1110-1712), after the
+// update kernels ran WITHOUT terms.  Inside the update kernels a term costs every warp that meets an
+// absorber row one dependent HBM round trip per term (~2.8 us under load) in front of its stores, and
+// terms on the y / z faces sit in every y-line tile: the all-face-CPML step ran 35-40 % slower than
+// the x-only one.  Here one thread = one (term, cell): the derivative the term consumes is fetched
+// again -- x differences and FDTD differences recomputed from F (unchanged during the half-step), z
+// derivatives from the spectral scratch, y derivatives from the side buffer the update phase saved
+// for the absorber rows -- then psi = b psi + a d ; G += sign C2 (kf d + psi), the reference's
+// statements in the reference's order (main update first, then faces y, z, x: one launch per axis,
+// the terms of one launch touch disjoint (cell, component) pairs).
+template <typename T, bool CPLX>
+__global__ void __launch_bounds__(256)
+k_pml_terms(const UpdParams p, const int t0, const long maxcells) {
+    using A = typename AccT<CPLX>::type;
+    using E = Elem<T, CPLX>;
+    const PmlTermDev& q = p.terms[t0 + blockIdx.y];
+    const int ex = q.hi[0] - q.lo[0], ey = q.hi[1] - q.lo[1], ez = q.hi[2] - q.lo[2];
+    const long ncell = (long)ex * ey * ez;
+    for (long tid = (long)blockIdx.x * blockDim.x + threadIdx.x; tid < ncell; tid += (long)gridDim.x * blockDim.x) {
+        const int k = q.lo[2] + (int)(tid % ez), j = q.lo[1] + (int)((tid / ez) % ey), i = q.lo[0] + (int)(tid / ((long)ez * ey));
+        const size_t plane = (size_t)p.ny * p.nz;
+        const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
+        const int dir = p.dir, df = q.diff;
+        A d = a_zero(A());
+        if (df == 3 || df == 4) {                       // d/dx F_z (3), d/dx F_y (4)
+            const int fc = df == 3 ? 2 : 1;
+            if (p.pstd) d = E::ld(p.dxs[df == 3 ? 0 : 1], idx);
+            else {
+                const int in = i + dir;
+                const double sx = dir > 0 ? p.rdx : -p.rdx;
+                if (in >= 0 && in < p.nx) d = a_scale(sx, a_sub(E::ld(p.F[fc], idx + (ptrdiff_t)dir * plane), E::ld(p.F[fc], idx)));
+                else if (p.halo[0] != nullptr)
+                    d = a_scale(sx, a_sub(E::ld(p.halo[df == 3 ? 1 : 0], (size_t)j * p.nz + k), E::ld(p.F[fc], idx)));
+            }
+        } else if (df == 1 || df == 2) {                // d/dz F_y (1), d/dz F_x (2)
+            if (p.fdtd) {
+                const int kn = k + dir, fc = df == 1 ? 1 : 0;
+                const double sz = dir > 0 ? p.rdz : -p.rdz;
+                if (kn >= 0 && kn < p.nz) d = a_scale(sz, a_sub(E::ld(p.F[fc], idx + (ptrdiff_t)dir), E::ld(p.F[fc], idx)));
+            } else d = E::ld(p.dz[df == 1 ? 0 : 1], (size_t)((long long)idx + p.dz_off));
+        } else {                                        // d/dy F_z (0), d/dy F_x (5)
+            if (p.fdtd) {
+                const int jn = j + dir, fc = df == 0 ? 2 : 0;
+                const double sy = dir > 0 ? p.rdy : -p.rdy;
+                if (jn >= 0 && jn < p.ny) d = a_scale(sy, a_sub(E::ld(p.F[fc], idx + (ptrdiff_t)dir * p.nz), E::ld(p.F[fc], idx)));
+            } else {
+                const int jj = j < p.ys_lo_n ? j : j - p.ys_hi_0 + p.ys_lo_n;
+                const size_t sidx = ((size_t)i * p.ys_rows + jj) * p.nz + k;
+                if constexpr (CPLX) {
+                    d = E::ld(p.dy_side, (df == 0 ? 0 : (size_t)p.nx * p.ys_rows * p.nz) + sidx);
+                } else {
+                    using C2 = typename std::conditional<std::is_same<T, float>::value, float2, double2>::type;
+                    const C2 v = ((const C2*)p.dy_side)[sidx];
+                    d = df == 0 ? (double)v.x : (double)v.y;
+                }
+            }
+        }
+        const int ax = q.axis;
+        const int n = (ax == 0 ? i - q.lo[0] : ax == 1 ? j - q.lo[1] : k - q.lo[2]);
+        const int pn = n + q.psi_off;
+        const int p0 = ax == 0 ? pn : i, p1 = ax == 1 ? pn : j, p2 = ax == 2 ? pn : k;
+        const size_t pidx = ((size_t)p0 * q.pdim[1] + p1) * q.pdim[2] + p2;
+        double cf[1];
+        if (p.Cidx) ld_coeff<1, true>(p, idx, cf); else ld_coeff<1, false>(p, idx, cf);
+        A psi = E::ld(q.psi, pidx);
+        psi = a_add(a_scale(q.b[n], psi), a_scale(q.a[n], d));
+        E::st(q.psi, pidx, psi);
+        psi = E::rnd(psi);
+        const A corr = a_scale(q.sign, a_scale(cf[0], a_add(a_scale(q.kf[n], d), psi)));
+        E::st(p.G[q.comp], idx, a_add(E::ld(p.G[q.comp], idx), corr));
+    }
+}
+
+template <typename T, bool CP>
+static int launch_pml_terms(ies_ctx* c, const UpdParams& p) {
+    // one launch per face axis in the reference's order y, z, x (terms are stored in that order)
+    int t = 0;
+    while (t < p.nterms) {
+        int t1 = t;
+        long maxc = 0;
+        while (t1 < p.nterms && p.terms[t1].axis == p.terms[t].axis) {
+            const PmlTermDev& q = p.terms[t1];
+            maxc = std::max(maxc, (long)(q.hi[0] - q.lo[0]) * (q.hi[1] - q.lo[1]) * (q.hi[2] - q.lo[2]));
+            ++t1;
+        }
+        if (maxc > 0) {
+            const unsigned gx = (unsigned)std::min<long>((maxc + 255) / 256, 148L * 32);
+            k_pml_terms<T, CP><<<dim3(gx, (unsigned)(t1 - t)), 256, 0, c->stream>>>(p, t, maxc);
+            count_launch();
+            IES_CUDA(cudaGetLastError());
+        }
+        t = t1;
+    }
+    return 0;
 }
 
 // Lossless palette compression of a coefficient array: distinct bit patterns are appended to
@@ -454,6 +551,8 @@ static int fill_params(ies_ctx* c, int half, UpdParams& p) {
     p.rdx = 1.0 / c->cfg.dx; p.rdy = 1.0 / c->cfg.dy; p.rdz = 1.0 / c->cfg.dz;
     p.nterms = (int)c->terms[half].size();
     for (int t = 0; t < p.nterms; ++t) p.terms[t] = c->terms[half][t];
+    p.dy_side = nullptr; p.ys_lo_n = 0; p.ys_hi_0 = p.ny; p.ys_rows = 0;
+    p.fdtd = c->cfg.method == IES_FDTD;
     return 0;
 }
 
@@ -498,9 +597,35 @@ static int do_update(ies_ctx* c, int half, int phase) {
     for (int t = 0; t < p.nterms; ++t) yz_pml |= p.terms[t].axis != 0;
     // ... and double precision (fp32: 2.32 vs 2.09 ms/step on 1024x256x256 -- half the bytes per tile, the
     // roles' fixed costs weigh twice as much)
-    const bool fused = fused_ok && (c->use_fused > 0 || (c->use_fused < 0 && c->cfg.ny <= 256 && !yz_pml && c->dbl));
+    // CPML corrections in a pass of their own (k_pml_terms): the update kernels then see no term at all
+    // (default: whenever a y or z face carries terms, and for x-only absorbers on slabs large enough that the
+    //  extra launch is noise -- headline 3.17 -> 3.13 ms/step; a 256x64x64 FDTD step is launch-bound)
+    const bool split = p.nterms > 0 && (c->use_pml_split > 0 ||
+                                        (c->use_pml_split < 0 && (yz_pml || (size_t)nx * ny * nz >= ((size_t)1 << 23))));
+    const bool fused = fused_ok && (c->use_fused > 0 || (c->use_fused < 0 && c->cfg.ny <= 256 && (!yz_pml || split) && c->dbl));
     const bool overlap_ok = c->cfg.method != IES_FDTD && !fused;
     if (!overlap_ok) { if (phase == 0) return 0; phase = -1; }       // everything in phase 1
+    if (split && c->cfg.method != IES_FDTD) {
+        // absorber rows of the y faces: the update phase saves their y derivatives for the correction pass
+        int lo_n = 0, hi_0 = ny;
+        for (int t = 0; t < p.nterms; ++t) {
+            const PmlTermDev& q = p.terms[t];
+            if (q.axis != 1 || q.hi[1] <= q.lo[1]) continue;
+            if (q.lo[1] < ny / 2) lo_n = std::max(lo_n, q.hi[1]); else hi_0 = std::min(hi_0, q.lo[1]);
+        }
+        if (lo_n > hi_0) { lo_n = ny; hi_0 = ny; }          // faces meet: every row is saved
+        const int rows = lo_n + (ny - hi_0);
+        if (rows > 0) {
+            const size_t need = (size_t)(CP ? 2 : 1) * nx * rows * nz * (c->dbl ? 16 : 8);
+            if (c->dy_side_bytes < need) {
+                if (dev_alloc(c, &c->dy_side, need, false)) return 1;       // (an outgrown buffer stays owned until destroy)
+                c->dy_side_bytes = need;
+            }
+            p.dy_side = c->dy_side; p.ys_lo_n = lo_n; p.ys_hi_0 = hi_0; p.ys_rows = rows;
+        }
+    }
+    UpdParams pm = p;                       // what the update kernels see
+    if (split) pm.nterms = 0;
     if (c->cfg.method == IES_FDTD) {
         // ghost copies on the differentiated field, axis order x, y, z (space.py:1798-1858)
         for (int a = 0; a < 3; ++a) {
@@ -522,29 +647,31 @@ static int do_update(ies_ctx* c, int half, int phase) {
         if (c->fdtd_vec && nz % V == 0) {
             dim3 blk(32, 8, 1);
             dim3 grid((nz + 32 * V - 1) / (32 * V), (ny + 7) / 8, nx);
-            if (p.Cidx) k_fdtd_vec<T, CP, true><<<grid, blk, 0, c->stream>>>(p);
-            else k_fdtd_vec<T, CP, false><<<grid, blk, 0, c->stream>>>(p);
+            if (p.Cidx) k_fdtd_vec<T, CP, true><<<grid, blk, 0, c->stream>>>(pm);
+            else k_fdtd_vec<T, CP, false><<<grid, blk, 0, c->stream>>>(pm);
         } else {
             dim3 blk(nz >= 64 ? 64 : 32, nz >= 64 ? 4 : 8, 1);
             dim3 grid((nz + blk.x - 1) / blk.x, (ny + blk.y - 1) / blk.y, nx);
-            if (p.Cidx) k_fdtd<T, CP, true><<<grid, blk, 0, c->stream>>>(p);
-            else k_fdtd<T, CP, false><<<grid, blk, 0, c->stream>>>(p);
+            if (p.Cidx) k_fdtd<T, CP, true><<<grid, blk, 0, c->stream>>>(pm);
+            else k_fdtd<T, CP, false><<<grid, blk, 0, c->stream>>>(pm);
         }
         prof_mark(c, PROF_FDTD, 1);
         count_launch();
         IES_CUDA(cudaGetLastError());
+        if (split) return launch_pml_terms<T, CP>(c, p);
         return 0;
     }
     for (int a = 1; a < 3; ++a)
         if (!c->mult[half][a]) { set_error("spectral multiplier not set (malloc()/init_update_constants() missing)"); return 1; }
     {
-        const bool ring_only = fused && c->fused_ring_planes > 0 && c->fused_ring_planes < c->cfg.nx;
+        const bool ring_only = fused && !split && c->fused_ring_planes > 0 && c->fused_ring_planes < c->cfg.nx;
         if (!ring_only && ensure_scratch(c, 0, c->cfg.method == IES_PSTD ? 3 : 1)) return 1;
     }
-    p.dz[0] = c->scratch[0]; p.dz[1] = c->scratch[1];
+    p.dz[0] = pm.dz[0] = c->scratch[0]; p.dz[1] = pm.dz[1] = c->scratch[1];
     if (fused) {
         // one launch: z-line tiles run LEAD planes ahead of the y-line update tiles (shpf_fused.cuh)
         int ring = c->fused_ring_planes;
+        if (split) ring = 0;                // the correction pass reads the z derivatives of the whole slab afterwards
         if (ring <= 0 || ring >= c->cfg.nx) ring = c->cfg.nx;
         if (ring < c->cfg.nx) {
             if (ring < c->fused_lead + 2) ring = c->fused_lead + 2;
@@ -553,17 +680,20 @@ static int do_update(ies_ctx* c, int half, int phase) {
                 for (int q = 0; q < 2; ++q) if (dev_alloc(c, &c->fused_ring[q], rb)) return 1;
                 c->fused_ring_alloc = ring;
             }
-            p.dz[0] = c->fused_ring[0]; p.dz[1] = c->fused_ring[1];
+            pm.dz[0] = c->fused_ring[0]; pm.dz[1] = c->fused_ring[1];
         }
         const int keep = c->fused_ring_planes;
         c->fused_ring_planes = ring;
-        const int rc = launch_shpf_fused<T, CP>(c, p, half);
+        const int rc = launch_shpf_fused<T, CP>(c, pm, half);
         c->fused_ring_planes = keep;
         if (rc == 1) return 1;
-        if (rc == 0) return post_ghost_x<T, CP>(c, p);
-        p.dz[0] = c->scratch[0]; p.dz[1] = c->scratch[1];       // no instantiation: two-kernel path
+        if (rc == 0) {
+            if (split && launch_pml_terms<T, CP>(c, p)) return 1;
+            return post_ghost_x<T, CP>(c, p);
+        }
+        pm.dz[0] = c->scratch[0]; pm.dz[1] = c->scratch[1];       // no instantiation: two-kernel path
     }
-    p.dxs[0] = c->scratch[2]; p.dxs[1] = c->scratch[3];
+    p.dxs[0] = pm.dxs[0] = c->scratch[2]; p.dxs[1] = pm.dxs[1] = c->scratch[3];
     if (phase != 1) {
         if (c->cfg.method == IES_PSTD) {
             if (!c->mult[half][0]) { set_error("x multiplier not set"); return 1; }
@@ -572,7 +702,8 @@ static int do_update(ies_ctx* c, int half, int phase) {
         if (launch_zline<T, CP>(c, p.F[1], p.F[0], c->scratch[0], c->scratch[1], half, 0, nx, 0)) return 1;
     }
     if (phase != 0) {
-        if (launch_yline_update<T, CP>(c, p, half)) return 1;
+        if (launch_yline_update<T, CP>(c, pm, half)) return 1;
+        if (split && launch_pml_terms<T, CP>(c, p)) return 1;
         if (post_ghost_x<T, CP>(c, p)) return 1;
     }
     return 0;
@@ -641,6 +772,8 @@ static int create_impl(const ies_config* cfg, ies_ctx* c) {
     if (const char* e = getenv("IES_B200_PALETTE")) c->use_palette = atoi(e);
     for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
     // spectral scratch is allocated on first use
+    c->use_pml_split = -1; c->dy_side = nullptr; c->dy_side_bytes = 0;
+    if (const char* e = getenv("IES_B200_PML_SPLIT")) c->use_pml_split = atoi(e);
     c->use_fused = -1; c->fused_zb = 2; c->fused_prefetch = 0; c->fused_lead = 6; c->fused_ring_planes = 0; c->fused_ring_alloc = 0;
     c->fused_ring[0] = c->fused_ring[1] = nullptr; c->fused_sync = nullptr; c->twz_t = nullptr; c->fused_prof = nullptr; c->fused_prof_mem = nullptr;
     if (const char* e = getenv("IES_B200_FUSED")) c->use_fused = atoi(e);
@@ -749,6 +882,7 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     if (n == "palette") c->use_palette = v;
     else if (n == "ctile") c->use_ctile = v;
     else if (n == "fdtd_vec") c->fdtd_vec = v;
+    else if (n == "pml_split") c->use_pml_split = v;
     else if (n == "fused") c->use_fused = v;
     else if (n == "fused_lead") c->fused_lead = v < 1 ? 1 : v;
     else if (n == "fused_zb") c->fused_zb = v == 2 ? 2 : 1;

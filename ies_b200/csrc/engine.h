@@ -44,6 +44,12 @@ struct UpdParams {
     long long dz_off;           // element offset of the dz scratch relative to the field index
     double rdx, rdy, rdz;
     Box box[3];
+    // y-derivative side buffer of the separate CPML pass (engine.cu k_pml_terms): the update phase of the
+    // spectral kernels saves (d/dy F_z, d/dy F_x) of the rows [0, ys_lo_n) and [ys_hi_0, ny) there,
+    // index ((f * nx + i) * ys_rows + jj) * nz + k with jj = j or j - ys_hi_0 + ys_lo_n; null = nothing to save
+    void* dy_side;
+    int ys_lo_n, ys_hi_0, ys_rows;
+    int fdtd;                   // derivatives are two-point differences (k_pml_terms recomputes them)
     int nterms;
     PmlTermDev terms[MAX_TERMS];
 };
@@ -92,6 +98,9 @@ struct Ctx {
     int profiling;                     // per-kernel CUDA-event timing on/off
     std::vector<cudaEvent_t> prof_ev[4][2];   // [slot][begin/end]
     // fused single-launch SHPF half-step (shpf_fused.cuh)
+    int use_pml_split;                 // CPML corrections: 1 = separate pass over the absorber cells (k_pml_terms),
+                                       // 0 = inside the update kernels, -1 (default) = separate when a y or z face has terms
+    void* dy_side; size_t dy_side_bytes;
     int use_fused;                     // 1 = k_shpf_fused where instantiated, 0 = k_zline + k_yline_update
     int fused_prefetch;                // z role prefetches F_z and G of its rows into L2 for the y role
     int fused_zb;                      // z tiles per z-role CTA (1 or 2)

@@ -249,6 +249,19 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
             } else {
                 ld_coeff<V, CM == 1>(p, idx, cf[u]);
             }
+            if (p.dy_side) {
+                // separate CPML pass (engine.cu k_pml_terms): keep the y derivatives of the absorber rows
+                const int jj = j < p.ys_lo_n ? j : (j >= p.ys_hi_0 ? j - p.ys_hi_0 + p.ys_lo_n : -1);
+                if (jj >= 0) {
+                    const size_t sidx = ((size_t)i * p.ys_rows + jj) * p.nz + k;
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        ((C*)p.dy_side)[sidx + v] = xbuf[(size_t)j * W + cg * V + v];
+                        if constexpr (CPLX)
+                            ((C*)p.dy_side)[(size_t)p.nx * p.ys_rows * p.nz + sidx + v] = xbuf[(size_t)N * W + (size_t)j * W + cg * V + v];
+                    }
+                }
+            }
         }
         // A tile spans all rows, so with CPML on the y faces every tile carries CPML terms; the
         // rows of this batch may still be interior: then they take the straight-line path too

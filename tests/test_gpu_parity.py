@@ -76,6 +76,29 @@ def test_fused_half_step_matches_two_kernel_path(product, name, ring, monkeypatc
         assert np.array_equal(np.asarray(a[n]), np.asarray(b[n])), n
 
 
+PML_SPLIT_CASES = ['shpf_f64_allpml', 'shpf_f64_allpml_r2', 'shpf_f64_ypml_only', 'shpf_f64_xpml', 'fdtd_f64_allpml',
+                   'fdtd_f64_allpml_r2', 'fdtd_f64_xpml_pbc', 'pstd_f64_allpml', 'pstd_c64_xpml', 'shpf_f64_allpml_64_r2',
+                   'shpf_f64_allpml_256_r2', 'shpf_f64_y512_z32', 'cfg5_shpf_24x512x512_sphere', 'shpf_f32_allpml_64']
+
+
+@pytest.mark.parametrize('name', PML_SPLIT_CASES)
+def test_separate_cpml_pass_matches_in_kernel_cpml(product, name, monkeypatch):
+    """CPML corrections applied by the separate pass over the absorber cells (k_pml_terms, default
+    when a y or z face carries terms) and inside the update kernels: same statements in the same
+    order, bit-identical in double precision.  Single-precision fields round G once more between
+    the main update and the corrections in the separate pass -- as the reference does
+    (space.py:801-803 then 1153-1162) -- so they agree to fp32 round-off."""
+    case = C.CASES_BY_NAME[name]
+    a = _run_with_env(product, case, monkeypatch, IES_B200_PML_SPLIT=1)
+    b = _run_with_env(product, case, monkeypatch, IES_B200_PML_SPLIT=0)
+    single = np.dtype(case['dtype']) in (np.dtype('float32'), np.dtype('complex64'))
+    for n in C.FIELDS:
+        if single:
+            assert max(C.group_rel_l2(a, b).values()) <= 1e-5
+        else:
+            assert np.array_equal(np.asarray(a[n]), np.asarray(b[n])), n
+
+
 def test_shpf_x_bloch_with_yz_bloch_is_refused(product):
     """The reference evaluates the y/z Bloch terms after the x ghost copies (space.py:1898-1930); the
     fused multiplier cannot, so the combination raises instead of returning different fields."""

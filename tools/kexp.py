@@ -24,6 +24,8 @@ import bench  # noqa: E402
 VARIANTS = [
     ('base', dict(fused=0)),                            # two-kernel path (k_zline + k_yline_update)
     ('fused', dict(fused=1)),                           # single launch, full-size scratch, defaults
+    ('fused_split', dict(fused=1, pml_split=1)),
+    ('base_split', dict(fused=0, pml_split=1)),
     ('fused_pf', dict(fused=1, fused_prefetch=1)),
     ('fused_l3', dict(fused=1, fused_lead=3)),
     ('fused_l10', dict(fused=1, fused_lead=10)),
@@ -33,8 +35,8 @@ VARIANTS = [
     ('noctile', dict(fused=0, ctile=0)),
     ('palette', dict(fused=0, palette=1, ctile=0)),
 ]
-ALL_OPTS = ('fused', 'fused_ring', 'fused_lead', 'fused_zb', 'fused_prefetch', 'palette', 'ctile')
-DEFAULTS = dict(fused=-1, fused_ring=0, fused_lead=6, fused_zb=2, fused_prefetch=0, palette=0, ctile=1)
+ALL_OPTS = ('fused', 'fused_ring', 'fused_lead', 'fused_zb', 'fused_prefetch', 'pml_split', 'palette', 'ctile')
+DEFAULTS = dict(fused=-1, fused_ring=0, fused_lead=6, fused_zb=2, fused_prefetch=0, pml_split=-1, palette=0, ctile=1)
 
 
 def main():
