@@ -74,13 +74,20 @@ int ies_destroy(ies_ctx* ctx);
  * non-blocking stream (use_own_stream = 1, cuda_stream ignored). */
 int ies_set_stream(ies_ctx* ctx, void* cuda_stream, int use_own_stream);
 int ies_sync(ies_ctx* ctx);
-/* Engine tuning knobs (no reference counterpart; defaults need no call).  Names:
- * "fused" (SHPF, real dtypes, ny == nz in {64,128,256,512}: 1 = the half-step as one launch,
- * z-line and y-line tiles as two roles of one grid [shpf_fused.cuh]; 0 = z-line derivative kernel +
- * y-line update kernel; -1 [default] = fused for lines up to 256 points, where it is faster), "fused_lead" (planes the z role runs ahead), "fused_ring" (scratch ring
- * size in planes, 0 = full-size scratch), "palette" (1 = palette-compressed coefficient arrays
- * when they hold <= 32 distinct values; default 0), "reset_psi" (zero the CPML auxiliary
- * arrays). */
+/* Engine tuning knobs (no reference counterpart; defaults need no call; every combination computes
+ * bit-identical fp64 fields).  Names:
+ *  "fused"      SHPF, real dtypes, ny == nz in {64,128,256,512}: 1 = the half-step as ONE launch, z-line and
+ *               y-line tiles as two roles of one grid [shpf_fused.cuh]; 0 = z-line derivative kernel +
+ *               y-line update kernel; -1 [default] = fused where it is faster (fp64, lines <= 256 points);
+ *  "fused_lead" planes the z role runs ahead (6); "fused_ring" scratch ring size in planes (0 = full-size
+ *               scratch); "fused_zb" z tiles per z-role CTA (2); "fused_prefetch" (0);
+ *  "pml_split"  CPML corrections: 1 = a separate pass over the absorber cells after the update kernels
+ *               [k_pml_terms], 0 = inside the update kernels, -1 [default] = separate when a y/z face carries
+ *               terms or the slab has >= 2^23 cells;
+ *  "ctile"      1 [default] = tiles whose cells share one coefficient skip the coefficient array;
+ *  "palette"    1 = palette-compressed coefficient arrays when they hold <= 32 distinct values (0);
+ *  "fdtd_vec"   1 [default] = 16-byte vectorised FDTD kernel when nz allows;
+ *  "reset_psi"  zero the CPML auxiliary arrays;  "fused_prof" development cycle counters. */
 int ies_set_option(ies_ctx* ctx, const char* name, int64_t value);
 
 /* ---- setup --------------------------------------------------------------- */
