@@ -193,7 +193,9 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 // coefficient array altogether: one array pass less for the HBM-bound kernel).
 // dz_off: element offset of the z-derivative scratch relative to the field index (0 for the
 // full-size scratch of the two-kernel path, the ring slot offset in the fused kernel).
-template <typename T, bool CPLX, int N, int CM, bool FAST>
+// SIDE: the tile saves the y derivatives of its absorber rows for the separate CPML pass (a template
+// parameter, not a run-time test: the test inside the load loop cost the headline path 5 %).
+template <typename T, bool CPLX, int N, int CM, bool FAST, bool SIDE>
 __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, const int k0, const unsigned mask,
                                               const int upd, const typename Cx<T>::type* xbuf, const double cuni,
                                               const long long dz_off) {
@@ -249,7 +251,7 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
             } else {
                 ld_coeff<V, CM == 1>(p, idx, cf[u]);
             }
-            if (p.dy_side) {
+            if constexpr (SIDE) {
                 // separate CPML pass (engine.cu k_pml_terms): keep the y derivatives of the absorber rows
                 const int jj = j < p.ys_lo_n ? j : (j >= p.ys_hi_0 ? j - p.ys_hi_0 + p.ys_lo_n : -1);
                 if (jj >= 0) {
@@ -374,10 +376,14 @@ __device__ __forceinline__ void yline_phase_b_dispatch(const UpdParams& p, const
     // per-tile uniform coefficient (engine.cu: k_tile_uniform), NaN when the tile is not uniform
     const double cuni = p.Ctile ? p.Ctile[(size_t)i * ntk + kb] : __longlong_as_double(0x7ff8000000000000LL);
     const bool fast = mask == 0u && upd >= 0;
-    if (fast && cuni == cuni) yline_phase_b<T, CPLX, N, 2, true>(p, i, k0, mask, upd, xbuf, cuni, dz_off);
-    else if (fast) yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), true>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
-    else if (cuni == cuni) yline_phase_b<T, CPLX, N, 2, false>(p, i, k0, mask, upd, xbuf, cuni, dz_off);   // CPML tile, one coefficient
-    else yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), false>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
+    auto run = [&](auto side) {
+        constexpr bool SD = decltype(side)::value;
+        if (fast && cuni == cuni) yline_phase_b<T, CPLX, N, 2, true, SD>(p, i, k0, mask, upd, xbuf, cuni, dz_off);
+        else if (fast) yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), true, SD>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
+        else if (cuni == cuni) yline_phase_b<T, CPLX, N, 2, false, SD>(p, i, k0, mask, upd, xbuf, cuni, dz_off);   // CPML tile, one coefficient
+        else yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), false, SD>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
+    };
+    if (p.dy_side) run(std::true_type{}); else run(std::false_type{});
 }
 
 template <typename T, bool CPLX, int N, bool PAL>

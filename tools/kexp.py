@@ -25,6 +25,8 @@ VARIANTS = [
     ('base', dict(fused=0)),                            # two-kernel path (k_zline + k_yline_update)
     ('fused', dict(fused=1)),                           # single launch, full-size scratch, defaults
     ('fused_split', dict(fused=1, pml_split=1)),
+    ('fused_nosplit', dict(fused=1, pml_split=0)),
+    ('fused_nosplit_zb1_l3', dict(fused=1, pml_split=0, fused_zb=1, fused_lead=3)),
     ('base_split', dict(fused=0, pml_split=1)),
     ('fused_pf', dict(fused=1, fused_prefetch=1)),
     ('fused_l3', dict(fused=1, fused_lead=3)),
