@@ -10,6 +10,7 @@
 #include <type_traits>
 
 #include "engine.h"
+#include "fft_dev.cuh"
 #include "update_dev.cuh"
 
 namespace ies {
@@ -217,6 +218,75 @@ __global__ void k_put_src(void* f, int ny, int nz, Box bx, double2 pulse, int ha
     if constexpr (CPLX) add = make_double2(vr, vi); else add = vr;
     if (hard) E::st(f, idx, add);
     else E::st(f, idx, a_add(E::ld(f, idx), add));
+}
+
+// ---- spectral axes of ANY length (the reference takes any N: space.py:145-162) -----------------
+// The FFT kernels cover powers of two in 16..512.  For every other length the derivative
+// ifft(M fft(x)) is applied as what it is, a circulant matrix: y_j = sum_k c[(j - k) mod N] x_k with
+// c = ifft(M) (host, ies_set_multiplier).  O(N) per cell instead of O(log N) -- the shipped 50^3
+// SHPF set-up costs 50 multiply-adds per derivative and cell -- but on the GPU, in the field
+// precision rules of the FFT path, with the same update / CPML code behind it (k_update_generic).
+template <typename T, bool CPLX>
+__global__ void __launch_bounds__(256)
+k_circ(const void* __restrict__ src, void* __restrict__ dst, const typename Cx<T>::type* __restrict__ c,
+       int nx, int ny, int nz, int axis) {
+    using A = typename AccT<CPLX>::type;
+    using E = Elem<T, CPLX>;
+    const size_t ncell = (size_t)nx * ny * nz;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ncell) return;
+    const int k = (int)(idx % nz), j = (int)((idx / nz) % ny), i = (int)(idx / ((size_t)nz * ny));
+    const int n = axis == 0 ? nx : axis == 1 ? ny : nz;
+    const int me = axis == 0 ? i : axis == 1 ? j : k;
+    const size_t stride = axis == 0 ? (size_t)ny * nz : axis == 1 ? (size_t)nz : 1;
+    const size_t base = idx - (size_t)me * stride;
+    // accumulate in the transform's precision (T), like the FFT path
+    T ar = 0, ai = 0;
+    int m = me;                                          // (me - q) mod n, walked downwards
+    for (int q = 0; q < n; ++q) {
+        const typename Cx<T>::type cc = c[m];
+        if constexpr (CPLX) {
+            const A x = E::ld(src, base + (size_t)q * stride);
+            ar = r_add(ar, r_sub(r_mul(cc.x, (T)x.x), r_mul(cc.y, (T)x.y)));
+            ai = r_add(ai, r_add(r_mul(cc.x, (T)x.y), r_mul(cc.y, (T)x.x)));
+        } else {
+            ar = r_fma(cc.x, (T)E::ld(src, base + (size_t)q * stride), ar);
+        }
+        m = m == 0 ? n - 1 : m - 1;
+    }
+    if constexpr (CPLX) E::st(dst, idx, make_double2((double)ar, (double)ai));
+    else E::st(dst, idx, (double)ar);
+}
+
+// cell update with all spectral derivatives read from scratch (direct-circulant path)
+template <typename T, bool CPLX, bool PAL>
+__global__ void __launch_bounds__(256) k_update_generic(const UpdParams p) {
+    using A = typename AccT<CPLX>::type;
+    using E = Elem<T, CPLX>;
+    const size_t ncell = (size_t)p.nx * p.ny * p.nz;
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ncell) return;
+    const int k = (int)(idx % p.nz), j = (int)((idx / p.nz) % p.ny), i = (int)(idx / ((size_t)p.nz * p.ny));
+    const size_t plane = (size_t)p.ny * p.nz;
+    A d[6];
+    d[0] = E::ld(p.dys[0], idx); d[5] = E::ld(p.dys[1], idx);
+    d[1] = E::ld(p.dz[0], idx);  d[2] = E::ld(p.dz[1], idx);
+    if (p.pstd) { d[3] = E::ld(p.dxs[0], idx); d[4] = E::ld(p.dxs[1], idx); }
+    else {
+        const int in = i + p.dir;
+        const double sx = p.dir > 0 ? p.rdx : -p.rdx;
+        if (in >= 0 && in < p.nx) {
+            const size_t nb = idx + (ptrdiff_t)p.dir * plane;
+            d[3] = a_scale(sx, a_sub(E::ld(p.F[2], nb), E::ld(p.F[2], idx)));
+            d[4] = a_scale(sx, a_sub(E::ld(p.F[1], nb), E::ld(p.F[1], idx)));
+        } else if (p.halo[0] != nullptr) {
+            const size_t nb = (size_t)j * p.nz + k;
+            d[3] = a_scale(sx, a_sub(E::ld(p.halo[1], nb), E::ld(p.F[2], idx)));
+            d[4] = a_scale(sx, a_sub(E::ld(p.halo[0], nb), E::ld(p.F[1], idx)));
+        } else { d[3] = a_zero(A()); d[4] = a_zero(A()); }
+    }
+    const unsigned mask = p.nterms ? ((1u << p.nterms) - 1u) : 0u;
+    cell_update<T, CPLX, PAL>(p, mask, i, j, k, d);
 }
 
 // CPML corrections as a pass of their own over the absorber cells (space.py:1110-1712), after the
@@ -543,6 +613,7 @@ static int fill_params(ies_ctx* c, int half, UpdParams& p) {
     p.halo[1] = nb ? c->halo_recv[half][1] : nullptr;
     p.dz[0] = c->scratch[0]; p.dz[1] = c->scratch[1];
     p.dxs[0] = c->scratch[2]; p.dxs[1] = c->scratch[3];
+    p.dys[0] = p.dys[1] = nullptr;
     p.nx = c->cfg.nx; p.ny = c->cfg.ny; p.nz = c->cfg.nz;
     p.dir = half == IES_HALF_H ? +1 : -1;
     p.i0 = 0; p.i1 = c->cfg.nx;
@@ -600,7 +671,7 @@ static int do_update(ies_ctx* c, int half, int phase) {
     // CPML corrections in a pass of their own (k_pml_terms): the update kernels then see no term at all
     // (default: whenever a y or z face carries terms, and for x-only absorbers on slabs large enough that the
     //  extra launch is noise -- headline 3.17 -> 3.13 ms/step; a 256x64x64 FDTD step is launch-bound)
-    const bool split = p.nterms > 0 && (c->use_pml_split > 0 ||
+    const bool split = p.nterms > 0 && !c->generic && (c->use_pml_split > 0 ||
                                         (c->use_pml_split < 0 && (yz_pml || (size_t)nx * ny * nz >= ((size_t)1 << 23))));
     const bool fused = fused_ok && (c->use_fused > 0 || (c->use_fused < 0 && c->cfg.ny <= 256 && (!yz_pml || split) && c->dbl));
     const bool overlap_ok = c->cfg.method != IES_FDTD && !fused;
@@ -663,6 +734,39 @@ static int do_update(ies_ctx* c, int half, int phase) {
     }
     for (int a = 1; a < 3; ++a)
         if (!c->mult[half][a]) { set_error("spectral multiplier not set (malloc()/init_update_constants() missing)"); return 1; }
+    if (c->generic) {
+        if (phase == 0) return 0;
+        using C = typename Cx<T>::type;
+        const size_t fbytes = (size_t)nx * ny * nz * c->esize;
+        for (int q = 0; q < 6; ++q) {
+            if ((q == 2 || q == 3) && c->cfg.method != IES_PSTD) continue;
+            if (!c->scratch[q]) if (dev_alloc(c, &c->scratch[q], fbytes)) return 1;
+        }
+        const size_t ncell = (size_t)nx * ny * nz;
+        const unsigned grid = (unsigned)((ncell + 255) / 256);
+        auto circ = [&](const void* src, void* dst, int axis) {
+            k_circ<T, CP><<<grid, 256, 0, c->stream>>>(src, dst, (const C*)c->circ[half][axis], nx, ny, nz, axis);
+            count_launch();
+        };
+        circ(p.F[1], c->scratch[0], 2); circ(p.F[0], c->scratch[1], 2);         // d/dz F_y, d/dz F_x
+        circ(p.F[2], c->scratch[4], 1); circ(p.F[0], c->scratch[5], 1);         // d/dy F_z, d/dy F_x
+        if (c->cfg.method == IES_PSTD) {
+            if (!c->circ[half][0]) { set_error("x multiplier not set"); return 1; }
+            circ(p.F[2], c->scratch[2], 0); circ(p.F[1], c->scratch[3], 0);     // d/dx F_z, d/dx F_y
+        }
+        UpdParams pg = p;                   // CPML inside the update (terms walk of cell_update)
+        pg.dz[0] = c->scratch[0]; pg.dz[1] = c->scratch[1];
+        pg.dxs[0] = c->scratch[2]; pg.dxs[1] = c->scratch[3];
+        pg.dys[0] = c->scratch[4]; pg.dys[1] = c->scratch[5];
+        pg.dy_side = nullptr;
+        prof_mark(c, PROF_YLINE_UPDATE, 0);
+        if (pg.Cidx) k_update_generic<T, CP, true><<<grid, 256, 0, c->stream>>>(pg);
+        else k_update_generic<T, CP, false><<<grid, 256, 0, c->stream>>>(pg);
+        prof_mark(c, PROF_YLINE_UPDATE, 1);
+        count_launch();
+        IES_CUDA(cudaGetLastError());
+        return post_ghost_x<T, CP>(c, p);
+    }
     {
         const bool ring_only = fused && !split && c->fused_ring_planes > 0 && c->fused_ring_planes < c->cfg.nx;
         if (!ring_only && ensure_scratch(c, 0, c->cfg.method == IES_PSTD ? 3 : 1)) return 1;
@@ -722,14 +826,7 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
     if (!cfg || !out) { set_error("null argument"); return 1; }
     if (cfg->nx < 1 || cfg->ny < 2 || cfg->nz < 2) { set_error("bad grid"); return 1; }
     if (cfg->dtype < 0 || cfg->dtype > 3 || cfg->method < 0 || cfg->method > 2) { set_error("bad dtype/method"); return 1; }
-    if (cfg->method != IES_FDTD) {
-        if (!fft_len_supported(cfg->ny) || !fft_len_supported(cfg->nz) ||
-            (cfg->method == IES_PSTD && !fft_len_supported(cfg->nx))) {
-            set_error("SHPF/PSTD need power-of-two FFT axes in 16..512 (got ny=" + std::to_string(cfg->ny) +
-                      ", nz=" + std::to_string(cfg->nz) + (cfg->method == IES_PSTD ? ", nx=" + std::to_string(cfg->nx) : "") + ")");
-            return 1;
-        }
-    }
+    if (cfg->method != IES_FDTD && (cfg->ny < 2 || cfg->nz < 2)) { set_error("bad grid"); return 1; }
     int ndev = 0;
     IES_CUDA(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) { set_error("no such CUDA device"); return 1; }
@@ -751,6 +848,11 @@ int ies_create(const ies_config* cfg, ies_ctx** out) {
 
 static int create_impl(const ies_config* cfg, ies_ctx* c) {
     c->cfg = *cfg;
+    // any spectral axis the FFT kernels do not cover switches the context to direct circulant sums
+    c->generic = cfg->method != IES_FDTD &&
+                 (!fft_len_supported(cfg->ny) || !fft_len_supported(cfg->nz) ||
+                  (cfg->method == IES_PSTD && !fft_len_supported(cfg->nx)));
+    for (int h = 0; h < 2; ++h) for (int a = 0; a < 3; ++a) c->circ[h][a] = nullptr;
     c->cplx = cfg->dtype >= 2;
     c->dbl = (cfg->dtype & 1) != 0;
     c->esize = (c->dbl ? 8 : 4) * (c->cplx ? 2 : 1);
@@ -770,7 +872,7 @@ static int create_impl(const ies_config* cfg, ies_ctx* c) {
     if (const char* e = getenv("IES_B200_CTILE")) c->use_ctile = atoi(e);
     c->use_palette = 0;     // measured slower than the f64 array (index -> value dependent loads), kept as an option
     if (const char* e = getenv("IES_B200_PALETTE")) c->use_palette = atoi(e);
-    for (int q = 0; q < 4; ++q) c->scratch[q] = nullptr;
+    for (int q = 0; q < 6; ++q) c->scratch[q] = nullptr;
     // spectral scratch is allocated on first use
     c->use_pml_split = -1; c->dy_side = nullptr; c->dy_side_bytes = 0;
     if (const char* e = getenv("IES_B200_PML_SPLIT")) c->use_pml_split = atoi(e);
@@ -800,7 +902,7 @@ static int create_impl(const ies_config* cfg, ies_ctx* c) {
     const int dims[3] = {cfg->nx, cfg->ny, cfg->nz};
     for (int a = 0; a < 3; ++a) {
         c->tw[a] = nullptr;
-        if (cfg->method == IES_FDTD || (a == 0 && cfg->method != IES_PSTD)) continue;
+        if (cfg->method == IES_FDTD || (a == 0 && cfg->method != IES_PSTD) || c->generic) continue;
         const int n = dims[a];
         std::vector<double> hd(2 * n);
         std::vector<float> hf(2 * n);
@@ -822,7 +924,7 @@ static int create_impl(const ies_config* cfg, ies_ctx* c) {
     // inverse stage NS = N/16; one table at N = 256): lines handled by adjacent lanes read them coalesced
     for (int a = 1; a < 3; ++a) {
         c->tw_t[a] = nullptr;
-        if (cfg->method == IES_FDTD) continue;
+        if (cfg->method == IES_FDTD || c->generic) continue;
         const int n = dims[a];
         if (n <= 16) continue;
         const int r1 = (n / 16 >= 16) ? 16 : n / 16, fwd = r1 * 16, nsi = n / 16, fstep = n / (16 * r1);
@@ -967,7 +1069,7 @@ int ies_set_coeff(ies_ctx* c, int half, const double* host, int64_t n) {
     IES_CUDA(cudaMemcpyAsync(c->C[half], host, ncell * 8, cudaMemcpyHostToDevice, c->stream));
     // palette form: materials are piecewise constant, so the array usually holds a handful of
     // distinct values; the update kernels then read one index byte per cell instead of 8 bytes
-    if (c->cfg.method != IES_FDTD) {
+    if (c->cfg.method != IES_FDTD && !c->generic) {
         // per-tile uniform coefficients for the y-line kernel (tile = 4096/ny columns of one plane)
         // = YCfg::W of spectral.cuh: 256 threads (128 for complex dtypes, lines up to 1024) / (ny/16)
 #ifndef IES_Y512_THREADS
@@ -1021,9 +1123,30 @@ int ies_set_update_box(ies_ctx* c, int comp, const int32_t lo[3], const int32_t 
 int ies_set_multiplier(ies_ctx* c, int half, int axis, const double* re_im, int32_t n) {
     const int dims[3] = {c->cfg.nx, c->cfg.ny, c->cfg.nz};
     if (half < 0 || half > 1 || axis < 0 || axis > 2 || n != dims[axis]) { set_error("ies_set_multiplier: bad args"); return 1; }
-    if (!fft_len_supported(n)) { set_error("ies_set_multiplier: unsupported length"); return 1; }
     IES_CUDA(cudaSetDevice(c->cfg.device));
     const size_t b = (size_t)2 * n * (c->dbl ? 8 : 4);
+    if (c->generic) {
+        // direct-circulant path: first column c = ifft(M), c[m] = (1/n) sum_k M[k] exp(+2 pi i k m / n)
+        std::vector<double> hd(2 * (size_t)n);
+        std::vector<float> hf(2 * (size_t)n);
+        const long double w = 2.0L * 3.14159265358979323846264338327950288L / (long double)n;
+        for (int m = 0; m < n; ++m) {
+            long double sr = 0, si = 0;
+            for (int k = 0; k < n; ++k) {
+                const long double ang = w * (long double)(((long long)k * m) % n);
+                const long double cr = cosl(ang), ci = sinl(ang);
+                sr += (long double)re_im[2 * k] * cr - (long double)re_im[2 * k + 1] * ci;
+                si += (long double)re_im[2 * k] * ci + (long double)re_im[2 * k + 1] * cr;
+            }
+            hd[2 * m] = (double)(sr / n); hd[2 * m + 1] = (double)(si / n);
+            hf[2 * m] = (float)hd[2 * m]; hf[2 * m + 1] = (float)hd[2 * m + 1];
+        }
+        if (!c->circ[half][axis]) if (dev_alloc(c, &c->circ[half][axis], b, false)) return 1;
+        IES_CUDA(cudaMemcpyAsync(c->circ[half][axis], c->dbl ? (void*)hd.data() : (void*)hf.data(), b, cudaMemcpyHostToDevice, c->stream));
+        IES_CUDA(cudaStreamSynchronize(c->stream));
+        c->mult[half][axis] = c->circ[half][axis];       // "multiplier is set" for the checks of do_update
+        return 0;
+    }
     if (!c->mult[half][axis]) if (dev_alloc(c, &c->mult[half][axis], b, false)) return 1;
     // fold the 1/N of the inverse transform into the table (exact: N is a power of two)
     std::vector<double> hd(2 * n);

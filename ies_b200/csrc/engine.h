@@ -37,6 +37,7 @@ struct UpdParams {
     const void* halo[2];        // neighbour planes of F_y, F_z (or null)
     const void* dz[2];          // scratch: d/dz F_y, d/dz F_x   (spectral methods)
     const void* dxs[2];         // scratch: d/dx F_z, d/dx F_y   (PSTD)
+    const void* dys[2];         // scratch: d/dy F_z, d/dy F_x   (direct-circulant path only)
     int nx, ny, nz;
     int dir;                    // +1: forward differences (updateH); -1: backward (updateE)
     int i0, i1;                 // x range handled by this launch
@@ -69,7 +70,9 @@ struct Ctx {
     double* Ctile[2];           // per-tile uniform coefficient of the y-line kernel's tiles (or null)
     int use_ctile;
     int fdtd_vec;               // FDTD: 16-byte vectorised kernel when nz allows (k_fdtd_vec)
-    void* scratch[4];           // dzA dzB dxA dxB
+    void* scratch[6];           // dzA dzB dxA dxB (+ dyA dyB on the direct-circulant path)
+    bool generic;               // a spectral axis is not a power of two in 16..512: derivatives by direct circulant sums
+    void* circ[2][3];           // [half][axis] first column of the derivative circulant (FFT-precision complex, n entries)
     void* halo_recv[2][2];      // [half][y|z] planes inside halo_block
     void* halo_block;           // one cudaMalloc: 4 recv planes + the arrival flags (one IPC handle)
     size_t halo_block_bytes;

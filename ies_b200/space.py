@@ -583,6 +583,11 @@ class Basic3D:
         if np.dtype(self.field_dtype).kind == 'c':
             assert m.size == n
             return m
+        if n % 2:
+            # irfftn without an explicit length returns 2*(bins-1) samples: the reference's real-field
+            # spectral derivative only works on even axes (space.py:145-162)
+            raise ValueError(f"real field dtype with an odd spectral axis ({n} points): use an even length "
+                             "or a complex field dtype")
         full = np.zeros(n, dtype=np.complex128)
         h = n // 2
         full[:h + 1] = m[:h + 1]

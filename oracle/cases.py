@@ -107,6 +107,14 @@ LIVE_CASES = [
     _case('shpf_f64_z512_y128', 'SHPF', 'float64', (12, 128, 512), steps=6, npml=4, pbc=PBC_YZ, bbc=NO, src='point'),
     _case('shpf_f64_y512_z32', 'SHPF', 'float64', (12, 512, 32), steps=6, npml=4, pml=ALLPML, src='point'),
     _case('shpf_c64_z512_y16', 'SHPF', 'complex64', (12, 16, 512), steps=6, npml=4, pbc=PBC_YZ, bbc=NO, src='point'),
+    # spectral axes that are not a power of two (the reference takes any N; the engine applies the derivative
+    # as a circulant sum there): the shipped 50^3 set-up's line length, mixed lengths, complex odd lengths
+    _case('shpf_f64_50cube', 'SHPF', 'float64', (30, 50, 50), steps=8, npml=4, pbc=PBC_YZ, bbc=NO),
+    _case('shpf_f64_allpml_20x36', 'SHPF', 'float64', (24, 20, 36), steps=10, npml=4, pml=ALLPML, src='point'),
+    _case('shpf_f32_24x40_r2', 'SHPF', 'float32', (24, 24, 40), steps=10, npml=4, pbc=PBC_YZ, bbc=NO, ranks=2),
+    _case('shpf_c128_bloch_odd', 'SHPF', 'complex128', (20, 21, 27), steps=8, bbc=BBC_YZ, pbc=NO, mmt=K1, src='point'),
+    _case('pstd_f64_20x24x36', 'PSTD', 'float64', (20, 24, 36), steps=8, npml=4, src='plane'),
+    _case('pstd_c128_bloch_odd', 'PSTD', 'complex128', (15, 18, 21), steps=6, pml=NOPML, bbc=BBC_ALL, pbc=NO, mmt=K3, src='point'),
     # sources on every kind of component (E_z, E_x, H_y, H_x; soft / hard; point / plane)
     _case('shpf_f64_src_ez', 'SHPF', 'float64', (24, 32, 32), steps=10, pbc=PBC_YZ, bbc=NO, src='point', src_field='Ez'),
     _case('shpf_f64_src_ex_hard', 'SHPF', 'float64', (24, 32, 32), steps=10, pml=ALLPML, src='point', src_field='Ex', put='hard'),

@@ -27,14 +27,22 @@ def test_constructor_asserts(product):
         mk(product, method='HPF')                          # unfinished in the reference, not offered here
 
 
-def test_spectral_axes_must_be_supported_fft_lengths(product):
-    from ies_b200 import _lib
-    with pytest.raises(_lib.EngineError) as e:
-        mk(product, grid=(32, 20, 16), gap=(720 * um / 32, 512 * um / 20, 512 * um / 16))
-    assert 'power-of-two' in str(e.value)
+def test_spectral_axes_of_any_length_are_accepted(product):
+    """The reference takes any N (space.py:145-162).  Powers of two in 16..512 run the FFT kernels, every
+    other length the direct-circulant path (parity: the *_50cube / *_odd cases of test_gpu_parity.py); a
+    real field dtype on an ODD axis is refused like the reference's irfftn would fail on it."""
+    sp = mk(product, grid=(32, 20, 16), gap=(720 * um / 32, 512 * um / 20, 512 * um / 16))
+    assert sp.Ex.shape == (32, 20, 16)
     sp = mk(product, grid=(30, 20, 18), method='FDTD', gap=(720 * um / 30, 512 * um / 20, 512 * um / 18),
             dt=0.25 * min(720 * um / 30, 512 * um / 20, 512 * um / 18) / 299792458.0)
     assert sp.Ex.shape == (30, 20, 18)                     # FDTD takes any grid
+    sp = mk(product, grid=(32, 21, 16), gap=(720 * um / 32, 512 * um / 21, 512 * um / 16))
+    sp.malloc()
+    sp.apply_PML({'x': '+-', 'y': '', 'z': ''}, 4)
+    sp.apply_BBC({'x': False, 'y': False, 'z': False}); sp.apply_PBC({'x': False, 'y': True, 'z': True})
+    sp.init_update_constants()
+    with pytest.raises(ValueError):
+        sp.updateH(0)
 
 
 def test_bloch_needs_complex_fields_and_a_setter(product):
@@ -78,9 +86,12 @@ def test_c_abi_reports_errors_instead_of_falling_back(product):
     ctx = C.c_void_p()
     assert lib.ies_create(C.byref(cfg), C.byref(ctx)) != 0
     assert b'device' in lib.ies_last_error()
-    cfg = _lib.Config(8, 24, 16, 1, 1, 0, 1, 0, 1e-6, 1e-6, 1e-6, 1e-16)      # ny = 24 with SHPF
+    cfg = _lib.Config(8, 1, 16, 1, 1, 0, 1, 0, 1e-6, 1e-6, 1e-6, 1e-16)       # a spectral axis of one point
     assert lib.ies_create(C.byref(cfg), C.byref(ctx)) != 0
-    assert b'power-of-two' in lib.ies_last_error()
+    assert b'bad grid' in lib.ies_last_error()
+    cfg = _lib.Config(8, 24, 16, 1, 1, 0, 1, 0, 1e-6, 1e-6, 1e-6, 1e-16)      # ny = 24 with SHPF: direct-circulant path
+    assert lib.ies_create(C.byref(cfg), C.byref(ctx)) == 0
+    assert lib.ies_destroy(ctx) == 0
     sp = mk(product)
     assert lib.ies_update_phase(sp._ctx, 5, 0) != 0                            # bad half
     assert lib.ies_set_option(sp._ctx, b'no_such_option', 1) != 0

@@ -273,3 +273,25 @@ def test_ipccomm_rendezvous_and_exchange_pattern(world, tmp_path):
     res = [q.get(timeout=120) for _ in ps]
     [p.join(60) for p in ps]
     assert all(ok for _, ok in res), res
+
+
+@pytest.mark.parametrize('n', [20, 50, 36])
+def test_full_multiplier_on_even_non_power_of_two_axes(n):
+    """Axes that are not a power of two take the engine's direct-circulant path; the host table is the
+    same Hermitian extension, and ifft(full * fft(x)) must equal the reference's irfft(m * rfft(x))."""
+    import types
+    from ies_b200.space import Basic3D
+    rng = np.random.default_rng(n)
+    d = 3.1e-6
+    k = np.fft.rfftfreq(n, d) * 2 * np.pi
+    ik = (1j * k).astype(np.complex128)
+    shift = np.exp(ik * d / 2)
+    self = types.SimpleNamespace(field_dtype=np.float64, mmtdtype=np.complex128)
+    full = Basic3D._full_multiplier(self, ik, shift, 0., n)
+    x = rng.standard_normal(n)
+    want = np.fft.irfft(ik * shift * np.fft.rfft(x), n)
+    got = np.fft.ifft(full * np.fft.fft(x))
+    assert np.max(np.abs(got.imag)) < 1e-9 * np.max(np.abs(want))
+    assert np.allclose(got.real, want, rtol=0, atol=1e-12 * np.max(np.abs(want)))
+    with pytest.raises(ValueError):
+        Basic3D._full_multiplier(self, ik, shift, 0., n + 1)
