@@ -299,84 +299,126 @@ __global__ void __launch_bounds__(256) k_update_generic(const UpdParams p) {
 // for the absorber rows -- then psi = b psi + a d ; G += sign C2 (kf d + psi), the reference's
 // statements in the reference's order (main update first, then faces y, z, x: one launch per axis,
 // the terms of one launch touch disjoint (cell, component) pairs).
-template <typename T, bool CPLX>
+// VW = cells per thread along z: Vec<T,CPLX>::V (16-byte accesses) when the term's box and the
+// arrays allow it (x and y faces on even grids), else 1.
+template <typename T, bool CPLX, int VW>
 __global__ void __launch_bounds__(256)
-k_pml_terms(const UpdParams p, const int t0, const long maxcells) {
+k_pml_terms(const UpdParams p, const int t0) {
     using A = typename AccT<CPLX>::type;
     using E = Elem<T, CPLX>;
+    using VV = Vec<T, CPLX>;
     const PmlTermDev& q = p.terms[t0 + blockIdx.y];
-    const int ex = q.hi[0] - q.lo[0], ey = q.hi[1] - q.lo[1], ez = q.hi[2] - q.lo[2];
-    const long ncell = (long)ex * ey * ez;
-    for (long tid = (long)blockIdx.x * blockDim.x + threadIdx.x; tid < ncell; tid += (long)gridDim.x * blockDim.x) {
-        const int k = q.lo[2] + (int)(tid % ez), j = q.lo[1] + (int)((tid / ez) % ey), i = q.lo[0] + (int)(tid / ((long)ez * ey));
-        const size_t plane = (size_t)p.ny * p.nz;
+    const int ax = q.axis, df = q.diff, dir = p.dir;
+    const unsigned ey = (unsigned)(q.hi[1] - q.lo[1]), ezv = (unsigned)(q.hi[2] - q.lo[2]) / VW;
+    const unsigned ngrp = (unsigned)(q.hi[0] - q.lo[0]) * ey * ezv;          // < 2^32 (checked by the launcher)
+    const size_t plane = (size_t)p.ny * p.nz;
+    // where the term's derivative comes from
+    const int fc = (df == 3 || df == 0) ? 2 : (df == 4 || df == 1) ? 1 : 0;  // F component differentiated
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < ngrp; g += gridDim.x * blockDim.x) {
+        const int k = q.lo[2] + (int)(g % ezv) * VW, j = q.lo[1] + (int)((g / ezv) % ey), i = q.lo[0] + (int)(g / (ezv * ey));
         const size_t idx = (size_t)i * plane + (size_t)j * p.nz + k;
-        const int dir = p.dir, df = q.diff;
-        A d = a_zero(A());
+        A d[VW];
+#pragma unroll
+        for (int v = 0; v < VW; ++v) d[v] = a_zero(A());
+        auto ldv = [&](const void* arr, size_t at, A (&o)[VW]) {
+            if constexpr (VW == 1) o[0] = E::ld(arr, at); else VV::ld(arr, at, o);
+        };
         if (df == 3 || df == 4) {                       // d/dx F_z (3), d/dx F_y (4)
-            const int fc = df == 3 ? 2 : 1;
-            if (p.pstd) d = E::ld(p.dxs[df == 3 ? 0 : 1], idx);
+            if (p.pstd) ldv(p.dxs[df == 3 ? 0 : 1], idx, d);
             else {
                 const int in = i + dir;
                 const double sx = dir > 0 ? p.rdx : -p.rdx;
-                if (in >= 0 && in < p.nx) d = a_scale(sx, a_sub(E::ld(p.F[fc], idx + (ptrdiff_t)dir * plane), E::ld(p.F[fc], idx)));
-                else if (p.halo[0] != nullptr)
-                    d = a_scale(sx, a_sub(E::ld(p.halo[df == 3 ? 1 : 0], (size_t)j * p.nz + k), E::ld(p.F[fc], idx)));
+                const bool inside = in >= 0 && in < p.nx;
+                if (inside || p.halo[0] != nullptr) {
+                    A a[VW], b[VW];
+                    if (inside) ldv(p.F[fc], idx + (ptrdiff_t)dir * plane, a);
+                    else ldv(p.halo[df == 3 ? 1 : 0], (size_t)j * p.nz + k, a);
+                    ldv(p.F[fc], idx, b);
+#pragma unroll
+                    for (int v = 0; v < VW; ++v) d[v] = a_scale(sx, a_sub(a[v], b[v]));
+                }
             }
         } else if (df == 1 || df == 2) {                // d/dz F_y (1), d/dz F_x (2)
             if (p.fdtd) {
-                const int kn = k + dir, fc = df == 1 ? 1 : 0;
                 const double sz = dir > 0 ? p.rdz : -p.rdz;
-                if (kn >= 0 && kn < p.nz) d = a_scale(sz, a_sub(E::ld(p.F[fc], idx + (ptrdiff_t)dir), E::ld(p.F[fc], idx)));
-            } else d = E::ld(p.dz[df == 1 ? 0 : 1], (size_t)((long long)idx + p.dz_off));
+#pragma unroll
+                for (int v = 0; v < VW; ++v) {
+                    const int kn = k + v + dir;
+                    if (kn >= 0 && kn < p.nz) d[v] = a_scale(sz, a_sub(E::ld(p.F[fc], idx + v + (ptrdiff_t)dir), E::ld(p.F[fc], idx + v)));
+                }
+            } else ldv(p.dz[df == 1 ? 0 : 1], (size_t)((long long)idx + p.dz_off), d);
         } else {                                        // d/dy F_z (0), d/dy F_x (5)
             if (p.fdtd) {
-                const int jn = j + dir, fc = df == 0 ? 2 : 0;
+                const int jn = j + dir;
                 const double sy = dir > 0 ? p.rdy : -p.rdy;
-                if (jn >= 0 && jn < p.ny) d = a_scale(sy, a_sub(E::ld(p.F[fc], idx + (ptrdiff_t)dir * p.nz), E::ld(p.F[fc], idx)));
+                if (jn >= 0 && jn < p.ny) {
+                    A a[VW], b[VW];
+                    ldv(p.F[fc], idx + (ptrdiff_t)dir * p.nz, a);
+                    ldv(p.F[fc], idx, b);
+#pragma unroll
+                    for (int v = 0; v < VW; ++v) d[v] = a_scale(sy, a_sub(a[v], b[v]));
+                }
             } else {
                 const int jj = j < p.ys_lo_n ? j : j - p.ys_hi_0 + p.ys_lo_n;
                 const size_t sidx = ((size_t)i * p.ys_rows + jj) * p.nz + k;
-                if constexpr (CPLX) {
-                    d = E::ld(p.dy_side, (df == 0 ? 0 : (size_t)p.nx * p.ys_rows * p.nz) + sidx);
-                } else {
-                    using C2 = typename std::conditional<std::is_same<T, float>::value, float2, double2>::type;
-                    const C2 v = ((const C2*)p.dy_side)[sidx];
-                    d = df == 0 ? (double)v.x : (double)v.y;
+#pragma unroll
+                for (int v = 0; v < VW; ++v) {
+                    if constexpr (CPLX) {
+                        d[v] = E::ld(p.dy_side, (df == 0 ? 0 : (size_t)p.nx * p.ys_rows * p.nz) + sidx + v);
+                    } else {
+                        using C2 = typename std::conditional<std::is_same<T, float>::value, float2, double2>::type;
+                        const C2 w = ((const C2*)p.dy_side)[sidx + v];
+                        d[v] = df == 0 ? (double)w.x : (double)w.y;
+                    }
                 }
             }
         }
-        const int ax = q.axis;
-        const int n = (ax == 0 ? i - q.lo[0] : ax == 1 ? j - q.lo[1] : k - q.lo[2]);
-        const int pn = n + q.psi_off;
+        // psi index of the first cell; the VW cells are adjacent in psi for x / y faces (VW > 1 only there)
+        const int n0 = (ax == 0 ? i - q.lo[0] : ax == 1 ? j - q.lo[1] : k - q.lo[2]);
+        const int pn = n0 + q.psi_off;
         const int p0 = ax == 0 ? pn : i, p1 = ax == 1 ? pn : j, p2 = ax == 2 ? pn : k;
         const size_t pidx = ((size_t)p0 * q.pdim[1] + p1) * q.pdim[2] + p2;
-        double cf[1];
-        if (p.Cidx) ld_coeff<1, true>(p, idx, cf); else ld_coeff<1, false>(p, idx, cf);
-        A psi = E::ld(q.psi, pidx);
-        psi = a_add(a_scale(q.b[n], psi), a_scale(q.a[n], d));
-        E::st(q.psi, pidx, psi);
-        psi = E::rnd(psi);
-        const A corr = a_scale(q.sign, a_scale(cf[0], a_add(a_scale(q.kf[n], d), psi)));
-        E::st(p.G[q.comp], idx, a_add(E::ld(p.G[q.comp], idx), corr));
+        double cf[VW];
+        if (p.Cidx) ld_coeff<VW, true>(p, idx, cf); else ld_coeff<VW, false>(p, idx, cf);
+        A psi[VW], gg[VW];
+        ldv(q.psi, pidx, psi);
+        ldv(p.G[q.comp], idx, gg);
+        const double tb = q.b[n0], ta = q.a[n0], tk = q.kf[n0];           // VW > 1: same n for the VW cells
+#pragma unroll
+        for (int v = 0; v < VW; ++v) {
+            psi[v] = a_add(a_scale(tb, psi[v]), a_scale(ta, d[v]));
+            const A pr = E::rnd(psi[v]);
+            gg[v] = a_add(gg[v], a_scale(q.sign, a_scale(cf[v], a_add(a_scale(tk, d[v]), pr))));
+        }
+        if constexpr (VW == 1) { E::st(q.psi, pidx, psi[0]); E::st(p.G[q.comp], idx, gg[0]); }
+        else { VV::st(q.psi, pidx, psi); VV::st(p.G[q.comp], idx, gg); }
     }
 }
 
 template <typename T, bool CP>
 static int launch_pml_terms(ies_ctx* c, const UpdParams& p) {
     // one launch per face axis in the reference's order y, z, x (terms are stored in that order)
+    constexpr int V = Vec<T, CP>::V;
     int t = 0;
     while (t < p.nterms) {
         int t1 = t;
         long maxc = 0;
+        bool vec = V > 1 && p.terms[t].axis != 2 && p.nz % V == 0;
         while (t1 < p.nterms && p.terms[t1].axis == p.terms[t].axis) {
             const PmlTermDev& q = p.terms[t1];
-            maxc = std::max(maxc, (long)(q.hi[0] - q.lo[0]) * (q.hi[1] - q.lo[1]) * (q.hi[2] - q.lo[2]));
+            const long cells = (long)(q.hi[0] - q.lo[0]) * (q.hi[1] - q.lo[1]) * (q.hi[2] - q.lo[2]);
+            if (cells >= (1L << 32)) { set_error("CPML box too large"); return 1; }
+            maxc = std::max(maxc, cells);
+            // 16-byte accesses need the z range to start and end on a vector boundary (psi of x / y faces has nz columns)
+            vec = vec && q.lo[2] % V == 0 && q.hi[2] % V == 0 && q.pdim[2] % V == 0;
             ++t1;
         }
         if (maxc > 0) {
-            const unsigned gx = (unsigned)std::min<long>((maxc + 255) / 256, 148L * 32);
-            k_pml_terms<T, CP><<<dim3(gx, (unsigned)(t1 - t)), 256, 0, c->stream>>>(p, t, maxc);
+            const long groups = vec ? maxc / V : maxc;
+            const unsigned gx = (unsigned)std::min<long>((groups + 255) / 256, 148L * 32);
+            const dim3 grid(gx, (unsigned)(t1 - t));
+            if (vec) k_pml_terms<T, CP, V><<<grid, 256, 0, c->stream>>>(p, t);
+            else k_pml_terms<T, CP, 1><<<grid, 256, 0, c->stream>>>(p, t);
             count_launch();
             IES_CUDA(cudaGetLastError());
         }

@@ -193,9 +193,7 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 // coefficient array altogether: one array pass less for the HBM-bound kernel).
 // dz_off: element offset of the z-derivative scratch relative to the field index (0 for the
 // full-size scratch of the two-kernel path, the ring slot offset in the fused kernel).
-// SIDE: the tile saves the y derivatives of its absorber rows for the separate CPML pass (a template
-// parameter, not a run-time test: the test inside the load loop cost the headline path 5 %).
-template <typename T, bool CPLX, int N, int CM, bool FAST, bool SIDE>
+template <typename T, bool CPLX, int N, int CM, bool FAST>
 __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, const int k0, const unsigned mask,
                                               const int upd, const typename Cx<T>::type* xbuf, const double cuni,
                                               const long long dz_off) {
@@ -250,19 +248,6 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
                 for (int v = 0; v < V; ++v) cf[u][v] = cuni;
             } else {
                 ld_coeff<V, CM == 1>(p, idx, cf[u]);
-            }
-            if constexpr (SIDE) {
-                // separate CPML pass (engine.cu k_pml_terms): keep the y derivatives of the absorber rows
-                const int jj = j < p.ys_lo_n ? j : (j >= p.ys_hi_0 ? j - p.ys_hi_0 + p.ys_lo_n : -1);
-                if (jj >= 0) {
-                    const size_t sidx = ((size_t)i * p.ys_rows + jj) * p.nz + k;
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        ((C*)p.dy_side)[sidx + v] = xbuf[(size_t)j * W + cg * V + v];
-                        if constexpr (CPLX)
-                            ((C*)p.dy_side)[(size_t)p.nx * p.ys_rows * p.nz + sidx + v] = xbuf[(size_t)N * W + (size_t)j * W + cg * V + v];
-                    }
-                }
             }
         }
         // A tile spans all rows, so with CPML on the y faces every tile carries CPML terms; the
@@ -361,6 +346,18 @@ __device__ __forceinline__ void yline_phase_a(const UpdParams& p, const int i, c
         __syncthreads();                 // everyone finished reading the exchange buffer
 #pragma unroll
         for (int q = 0; q < 16; ++q) xb.st(line_index<N>(t, q), v[q]);
+        if (p.dy_side && ok) {
+            // separate CPML pass (engine.cu k_pml_terms): the y derivatives of the absorber rows go to the
+            // side buffer straight from the registers (lane = column: 16-byte stores, contiguous per row).
+            // Doing this inside the update phase's load loop cost that phase 12 %.
+            C* side = (C*)p.dy_side + (size_t)f * p.nx * p.ys_rows * p.nz + (size_t)i * p.ys_rows * p.nz + k;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const int row = line_index<N>(t, q);
+                const int jj = row < p.ys_lo_n ? row : (row >= p.ys_hi_0 ? row - p.ys_hi_0 + p.ys_lo_n : -1);
+                if (jj >= 0) side[(size_t)jj * p.nz] = v[q];
+            }
+        }
     }
 }
 
@@ -376,14 +373,10 @@ __device__ __forceinline__ void yline_phase_b_dispatch(const UpdParams& p, const
     // per-tile uniform coefficient (engine.cu: k_tile_uniform), NaN when the tile is not uniform
     const double cuni = p.Ctile ? p.Ctile[(size_t)i * ntk + kb] : __longlong_as_double(0x7ff8000000000000LL);
     const bool fast = mask == 0u && upd >= 0;
-    auto run = [&](auto side) {
-        constexpr bool SD = decltype(side)::value;
-        if (fast && cuni == cuni) yline_phase_b<T, CPLX, N, 2, true, SD>(p, i, k0, mask, upd, xbuf, cuni, dz_off);
-        else if (fast) yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), true, SD>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
-        else if (cuni == cuni) yline_phase_b<T, CPLX, N, 2, false, SD>(p, i, k0, mask, upd, xbuf, cuni, dz_off);   // CPML tile, one coefficient
-        else yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), false, SD>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
-    };
-    if (p.dy_side) run(std::true_type{}); else run(std::false_type{});
+    if (fast && cuni == cuni) yline_phase_b<T, CPLX, N, 2, true>(p, i, k0, mask, upd, xbuf, cuni, dz_off);
+    else if (fast) yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), true>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
+    else if (cuni == cuni) yline_phase_b<T, CPLX, N, 2, false>(p, i, k0, mask, upd, xbuf, cuni, dz_off);   // CPML tile, one coefficient
+    else yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), false>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
 }
 
 template <typename T, bool CPLX, int N, bool PAL>
