@@ -660,7 +660,7 @@ static int fill_params(ies_ctx* c, int half, UpdParams& p) {
     p.dir = half == IES_HALF_H ? +1 : -1;
     p.i0 = 0; p.i1 = c->cfg.nx;
     p.pstd = c->cfg.method == IES_PSTD;
-    p.dz_off = 0;
+    p.dz_off = 0; p.dz_discard = 0;
     p.rdx = 1.0 / c->cfg.dx; p.rdy = 1.0 / c->cfg.dy; p.rdz = 1.0 / c->cfg.dz;
     p.nterms = (int)c->terms[half].size();
     for (int t = 0; t < p.nterms; ++t) p.terms[t] = c->terms[half][t];
@@ -828,6 +828,10 @@ static int do_update(ies_ctx* c, int half, int phase) {
             }
             pm.dz[0] = c->fused_ring[0]; pm.dz[1] = c->fused_ring[1];
         }
+        // the scratch is dead once the y role has read it, unless the correction pass differentiates along z
+        bool z_terms = false;
+        for (int t = 0; t < p.nterms; ++t) z_terms |= p.terms[t].axis == 2;
+        pm.dz_discard = (c->fused_discard && !(split && z_terms)) ? 1 : 0;
         const int keep = c->fused_ring_planes;
         c->fused_ring_planes = ring;
         const int rc = launch_shpf_fused<T, CP>(c, pm, half);
@@ -838,6 +842,7 @@ static int do_update(ies_ctx* c, int half, int phase) {
             return post_ghost_x<T, CP>(c, p);
         }
         pm.dz[0] = c->scratch[0]; pm.dz[1] = c->scratch[1];       // no instantiation: two-kernel path
+        pm.dz_discard = 0;
     }
     p.dxs[0] = pm.dxs[0] = c->scratch[2]; p.dxs[1] = pm.dxs[1] = c->scratch[3];
     if (phase != 1) {
@@ -918,7 +923,7 @@ static int create_impl(const ies_config* cfg, ies_ctx* c) {
     // spectral scratch is allocated on first use
     c->use_pml_split = -1; c->dy_side = nullptr; c->dy_side_bytes = 0;
     if (const char* e = getenv("IES_B200_PML_SPLIT")) c->use_pml_split = atoi(e);
-    c->use_fused = -1; c->fused_zb = 2; c->fused_prefetch = 0; c->fused_lead = 6; c->fused_ring_planes = 0; c->fused_ring_alloc = 0;
+    c->use_fused = -1; c->fused_zb = 2; c->fused_prefetch = 0; c->fused_discard = 1; c->fused_lead = 6; c->fused_ring_planes = 0; c->fused_ring_alloc = 0;
     c->fused_ring[0] = c->fused_ring[1] = nullptr; c->fused_sync = nullptr; c->twz_t = nullptr; c->fused_prof = nullptr; c->fused_prof_mem = nullptr;
     if (const char* e = getenv("IES_B200_FUSED")) c->use_fused = atoi(e);
     if (const char* e = getenv("IES_B200_FUSED_LEAD")) c->fused_lead = std::max(1, atoi(e));
@@ -1031,6 +1036,7 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     else if (n == "fused_lead") c->fused_lead = v < 1 ? 1 : v;
     else if (n == "fused_zb") c->fused_zb = v == 2 ? 2 : 1;
     else if (n == "fused_prefetch") c->fused_prefetch = v;
+    else if (n == "fused_discard") c->fused_discard = v;
     else if (n == "fused_ring") c->fused_ring_planes = v;
     else if (n == "fused_prof") {               // 1: start (zeroed) per-phase cycle counters, 0: stop
         if (v && !c->fused_prof_mem) { void* q; if (dev_alloc(c, &q, 16 * 8)) return 1; c->fused_prof_mem = (unsigned long long*)q; }

@@ -42,6 +42,7 @@ struct UpdParams {
     int dir;                    // +1: forward differences (updateH); -1: backward (updateE)
     int i0, i1;                 // x range handled by this launch
     int pstd;                   // x derivative comes from dxs[]
+    int dz_discard;             // fused kernel: drop the consumed dz scratch lines from L2 (discard.global.L2), no write-back
     long long dz_off;           // element offset of the dz scratch relative to the field index
     double rdx, rdy, rdz;
     Box box[3];
@@ -106,6 +107,7 @@ struct Ctx {
     void* dy_side; size_t dy_side_bytes;
     int use_fused;                     // 1 = k_shpf_fused where instantiated, 0 = k_zline + k_yline_update
     int fused_prefetch;                // z role prefetches F_z and G of its rows into L2 for the y role
+    int fused_discard;                 // y role discards the dz scratch lines it consumed (no DRAM write-back of the scratch)
     int fused_zb;                      // z tiles per z-role CTA (1 or 2)
     int fused_lead, fused_ring_planes; // planes of lead of the z role; scratch ring size in planes
     unsigned* fused_sync;              // ticket + zdone[nx] + ydone[nx]

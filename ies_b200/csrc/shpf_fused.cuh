@@ -214,7 +214,7 @@ k_shpf_fused(const UpdParams p, const FusedParams fp,
         fprof(fp, 4, &t0);
         const long long plane = (long long)p.ny * p.nz;
         const long long dz_off = ((long long)(i % fp.ring) - (long long)i) * plane;
-        yline_phase_b_dispatch<T, CPLX, NY, false>(p, i, kb, fp.yt, xbuf, dz_off);
+        yline_phase_b_dispatch<T, CPLX, NY, false, true>(p, i, kb, fp.yt, xbuf, dz_off);
         // only a z tile that re-uses this plane's ring slot waits for it
         if (i + fp.ring < p.i1) signal_counter(fp.ydone + i);
         fprof(fp, 5, &t0);

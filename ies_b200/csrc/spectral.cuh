@@ -193,7 +193,8 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 // coefficient array altogether: one array pass less for the HBM-bound kernel).
 // dz_off: element offset of the z-derivative scratch relative to the field index (0 for the
 // full-size scratch of the two-kernel path, the ring slot offset in the fused kernel).
-template <typename T, bool CPLX, int N, int CM, bool FAST>
+// DISC: compiled with the scratch-line discard of the fused kernel (run-time switch p.dz_discard).
+template <typename T, bool CPLX, int N, int CM, bool FAST, bool DISC = false>
 __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, const int k0, const unsigned mask,
                                               const int upd, const typename Cx<T>::type* xbuf, const double cuni,
                                               const long long dz_off) {
@@ -298,6 +299,16 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
             // ld.cs / L1::no_allocate / ld.cg on the streaming operands cost 8-13 %)
 #pragma unroll
             for (int c = 0; c < 3; ++c) vst_stream<VV>(p.G[c], idx, g[u][c], 0);
+            if constexpr (DISC && !CPLX && sizeof(T) == 8) {
+                // fused kernel: this tile was the only reader of its z-derivative scratch lines (a row segment of
+                // the tile is whole 128-byte lines, read by lanes of this warp in the load above): drop them from
+                // L2 so the dirty lines are never written back to HBM
+                if (p.dz_discard && (cg * V) % 16 == 0) {
+                    const size_t e = (size_t)((long long)idx + dz_off);
+                    asm volatile("discard.global.L2 [%0], 128;" :: "l"((const double*)p.dz[0] + e) : "memory");
+                    asm volatile("discard.global.L2 [%0], 128;" :: "l"((const double*)p.dz[1] + e) : "memory");
+                }
+            }
         }
     }
 }
@@ -363,7 +374,7 @@ __device__ __forceinline__ void yline_phase_a(const UpdParams& p, const int i, c
 
 // phase B for the tile (plane i, column block kb of ntk): picks the straight-line / uniform-
 // coefficient variants per tile.
-template <typename T, bool CPLX, int N, bool PAL>
+template <typename T, bool CPLX, int N, bool PAL, bool DISC = false>
 __device__ __forceinline__ void yline_phase_b_dispatch(const UpdParams& p, const int i, const int kb, const int ntk,
                                                        const typename Cx<T>::type* xbuf, const long long dz_off) {
     constexpr int W = YCfg<T, CPLX, N>::W;
@@ -373,10 +384,10 @@ __device__ __forceinline__ void yline_phase_b_dispatch(const UpdParams& p, const
     // per-tile uniform coefficient (engine.cu: k_tile_uniform), NaN when the tile is not uniform
     const double cuni = p.Ctile ? p.Ctile[(size_t)i * ntk + kb] : __longlong_as_double(0x7ff8000000000000LL);
     const bool fast = mask == 0u && upd >= 0;
-    if (fast && cuni == cuni) yline_phase_b<T, CPLX, N, 2, true>(p, i, k0, mask, upd, xbuf, cuni, dz_off);
-    else if (fast) yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), true>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
-    else if (cuni == cuni) yline_phase_b<T, CPLX, N, 2, false>(p, i, k0, mask, upd, xbuf, cuni, dz_off);   // CPML tile, one coefficient
-    else yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), false>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
+    if (fast && cuni == cuni) yline_phase_b<T, CPLX, N, 2, true, DISC>(p, i, k0, mask, upd, xbuf, cuni, dz_off);
+    else if (fast) yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), true, DISC>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
+    else if (cuni == cuni) yline_phase_b<T, CPLX, N, 2, false, DISC>(p, i, k0, mask, upd, xbuf, cuni, dz_off);   // CPML tile, one coefficient
+    else yline_phase_b<T, CPLX, N, (PAL ? 1 : 0), false, DISC>(p, i, k0, mask, upd, xbuf, 0.0, dz_off);
 }
 
 template <typename T, bool CPLX, int N, bool PAL>
