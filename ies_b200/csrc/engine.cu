@@ -660,7 +660,7 @@ static int fill_params(ies_ctx* c, int half, UpdParams& p) {
     p.dir = half == IES_HALF_H ? +1 : -1;
     p.i0 = 0; p.i1 = c->cfg.nx;
     p.pstd = c->cfg.method == IES_PSTD;
-    p.dz_off = 0; p.dz_discard = 0;
+    p.dz_off = 0; p.dz_discard = 0; p.dz_keep_lo = 0; p.dz_keep_hi = (short)std::min(p.nz, 32767);
     p.rdx = 1.0 / c->cfg.dx; p.rdy = 1.0 / c->cfg.dy; p.rdz = 1.0 / c->cfg.dz;
     p.nterms = (int)c->terms[half].size();
     for (int t = 0; t < p.nterms; ++t) p.terms[t] = c->terms[half][t];
@@ -828,10 +828,16 @@ static int do_update(ies_ctx* c, int half, int phase) {
             }
             pm.dz[0] = c->fused_ring[0]; pm.dz[1] = c->fused_ring[1];
         }
-        // the scratch is dead once the y role has read it, unless the correction pass differentiates along z
-        bool z_terms = false;
-        for (int t = 0; t < p.nterms; ++t) z_terms |= p.terms[t].axis == 2;
-        pm.dz_discard = (c->fused_discard && !(split && z_terms)) ? 1 : 0;
+        // the scratch is dead once the y role has read it, except the columns of the z-face absorbers when the
+        // correction pass runs afterwards (it differentiates along z there)
+        pm.dz_discard = c->fused_discard ? 1 : 0;
+        pm.dz_keep_lo = 0; pm.dz_keep_hi = (short)nz;        // (fused: nz <= 512)
+        if (split)
+            for (int t = 0; t < p.nterms; ++t) {
+                const PmlTermDev& q = p.terms[t];
+                if (q.axis != 2 || q.hi[2] <= q.lo[2]) continue;
+                if (q.lo[2] < nz / 2) pm.dz_keep_lo = (short)std::max((int)pm.dz_keep_lo, q.hi[2]); else pm.dz_keep_hi = (short)std::min((int)pm.dz_keep_hi, q.lo[2]);
+            }
         const int keep = c->fused_ring_planes;
         c->fused_ring_planes = ring;
         const int rc = launch_shpf_fused<T, CP>(c, pm, half);
@@ -965,7 +971,7 @@ static int create_impl(const ies_config* cfg, ies_ctx* c) {
     }
     if (cfg->method == IES_SHPF) {
         // fused half-step: ticket + per-plane counters
-        void* q; if (dev_alloc(c, &q, sizeof(unsigned) * (size_t)(1 + 2 * cfg->nx))) return 1; c->fused_sync = (unsigned*)q;
+        void* q; if (dev_alloc(c, &q, sizeof(unsigned) * (size_t)(1 + 2 * cfg->nx + 32 * cfg->nx))) return 1; c->fused_sync = (unsigned*)q;
     }
     // stage tables of the y and z axes transposed to [m][jj] (fft_dev.cuh TwTables: forward stage NS = 16,
     // inverse stage NS = N/16; one table at N = 256): lines handled by adjacent lanes read them coalesced

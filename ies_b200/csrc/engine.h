@@ -53,6 +53,7 @@ struct UpdParams {
     int ys_lo_n, ys_hi_0, ys_rows;
     int fdtd;                   // derivatives are two-point differences (k_pml_terms recomputes them)
     int nterms;
+    short dz_keep_lo, dz_keep_hi;   // dz_discard: only lines with columns inside [dz_keep_lo, dz_keep_hi) are dropped (the CPML pass reads the rest)
     PmlTermDev terms[MAX_TERMS];
 };
 

@@ -108,11 +108,40 @@ template <int N> using Plan = PlanV<N, 16>;
 // LOAD : read inputs from the exchange buffer;  STORE: write outputs to it at
 //   (j/NS)*NS*R + (j%NS) + m*NS.   Without STORE the outputs stay in v[b*R+m].
 // tw: master twiddle table W_N[k] = exp(-2 pi i k/N) (shared or global memory).
-template <int N, int VPT, int R, int NS, bool INV, bool LOAD, bool STORE, bool TWT = false, typename C, typename X>
+// X::SPLIT (XchgContigSplit): the buffer holds one real per element; a STORE stage writes the real
+// parts and leaves the imaginary parts in v[].y, the LOAD of the next stage (which is told that
+// stage's radix PR and stride PNS) reads the real parts, then passes the imaginary parts through
+// the same buffer.  Same values, same arithmetic -- only the route through shared memory differs.
+template <int N, int VPT, int R, int NS, bool INV, bool LOAD, bool STORE, bool TWT = false, int PR = 1, int PNS = 1,
+          typename C, typename X>
 __device__ __forceinline__ void fft_stage_v(C (&v)[VPT], const int t, const C* __restrict__ tw, X& xb) {
     constexpr int T = N / VPT;
     constexpr int NB = VPT / R;
-    if (LOAD) {
+    if constexpr (LOAD && X::SPLIT) {
+        decltype(v[0].x) re[VPT];
+        xb.sync();
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int j = t + T * b;
+#pragma unroll
+            for (int m = 0; m < R; ++m) re[b * R + m] = xb.ldx(j + m * (N / R));
+        }
+        xb.sync();
+#pragma unroll
+        for (int b = 0; b < VPT / PR; ++b) {
+            const int j = t + T * b;
+            const int base = (j / PNS) * PNS * PR + (j & (PNS - 1));
+#pragma unroll
+            for (int m = 0; m < PR; ++m) xb.stx(base + m * PNS, v[b * PR + m].y);
+        }
+        xb.sync();
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int j = t + T * b;
+#pragma unroll
+            for (int m = 0; m < R; ++m) { v[b * R + m].x = re[b * R + m]; v[b * R + m].y = xb.ldx(j + m * (N / R)); }
+        }
+    } else if (LOAD) {
         xb.sync();
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
@@ -141,7 +170,11 @@ __device__ __forceinline__ void fft_stage_v(C (&v)[VPT], const int t, const C* _
             }
         }
         Dft<R, INV, C>::run(in, out);
-        if (STORE) {
+        if constexpr (STORE && X::SPLIT) {
+            const int base = (j / NS) * NS * R + (j & (NS - 1));
+#pragma unroll
+            for (int m = 0; m < R; ++m) { xb.stx(base + m * NS, out[m].x); v[b * R + m].y = out[m].y; }
+        } else if (STORE) {
             const int base = (j / NS) * NS * R + (j & (NS - 1));
 #pragma unroll
             for (int m = 0; m < R; ++m) xb.st(base + m * NS, out[m]);
@@ -183,10 +216,10 @@ __device__ __forceinline__ void fft_forward_v(C (&v)[VPT], int t, const C* tw, X
     } else {
         fft_stage_v<N, VPT, VPT, 1, false, false, true>(v, t, tw, xb);
         if (P::R2 == 1) {
-            fft_stage_v<N, VPT, P::R1, VPT, false, true, false, TWT>(v, t, TWT ? twf : tw, xb);
+            fft_stage_v<N, VPT, P::R1, VPT, false, true, false, TWT, VPT, 1>(v, t, TWT ? twf : tw, xb);
         } else {
-            fft_stage_v<N, VPT, P::R1, VPT, false, true, true, TWT>(v, t, TWT ? twf : tw, xb);
-            fft_stage_v<N, VPT, (P::R2 > 1 ? P::R2 : 2), VPT * P::R1, false, true, false>(v, t, tw, xb);
+            fft_stage_v<N, VPT, P::R1, VPT, false, true, true, TWT, VPT, 1>(v, t, TWT ? twf : tw, xb);
+            fft_stage_v<N, VPT, (P::R2 > 1 ? P::R2 : 2), VPT * P::R1, false, true, false, false, P::R1, VPT>(v, t, tw, xb);
         }
     }
 }
@@ -198,12 +231,12 @@ __device__ __forceinline__ void fft_inverse_v(C (&v)[VPT], int t, const C* tw, X
         fft_stage_v<N, VPT, VPT, 1, true, false, false>(v, t, tw, xb);
     } else if (P::R2 == 1) {
         fft_stage_v<N, VPT, P::R1, 1, true, false, true>(v, t, tw, xb);
-        fft_stage_v<N, VPT, VPT, P::R1, true, true, false, TWT>(v, t, TWT ? twi : tw, xb);
+        fft_stage_v<N, VPT, VPT, P::R1, true, true, false, TWT, P::R1, 1>(v, t, TWT ? twi : tw, xb);
     } else {
         constexpr int R2 = (P::R2 > 1 ? P::R2 : 2);
         fft_stage_v<N, VPT, R2, 1, true, false, true>(v, t, tw, xb);
-        fft_stage_v<N, VPT, P::R1, R2, true, true, true>(v, t, tw, xb);
-        fft_stage_v<N, VPT, VPT, R2 * P::R1, true, true, false, TWT>(v, t, TWT ? twi : tw, xb);
+        fft_stage_v<N, VPT, P::R1, R2, true, true, true, false, R2, 1>(v, t, tw, xb);
+        fft_stage_v<N, VPT, VPT, R2 * P::R1, true, true, false, TWT, P::R1, R2>(v, t, TWT ? twi : tw, xb);
     }
 }
 
@@ -219,6 +252,7 @@ __device__ __forceinline__ void fft_inverse(C (&v)[16], int t, const C* tw, X& x
 // Contiguous lines (z axis): threads of a line are adjacent lanes; one line per
 // T lanes; padded by one element per 16 to keep the radix-16 scatter conflict free.
 template <typename C, int N> struct XchgContig {
+    static constexpr bool SPLIT = false;
     C* base;            // this line's slice of the exchange buffer
     static constexpr int LS = N + N / 16;
     __device__ __forceinline__ C ld(int i) const { return base[i + (i >> 4)]; }
@@ -229,6 +263,7 @@ template <typename C, int N> struct XchgContig {
 };
 // Same for the radix-8 plan: one pad element per 8 keeps the radix-8 scatter (8t + m) conflict free.
 template <typename C, int N> struct XchgContig8 {
+    static constexpr bool SPLIT = false;
     C* base;
     static constexpr int LS = N + N / 8;
     __device__ __forceinline__ C ld(int i) const { return base[i + (i >> 3)]; }
@@ -241,6 +276,7 @@ template <typename C, int N> struct XchgContig8 {
 // the radix-16 scatter (16t + m) and the strided gather (t + 16m) conflict free while a line
 // occupies exactly N elements (k_zline_update keeps its tile at 64 KB).
 template <typename C, int N> struct XchgContigSw {
+    static constexpr bool SPLIT = false;
     C* base;
     static constexpr int LS = N;
     static __device__ __forceinline__ int phys(int i) { return i ^ ((i >> 4) & 15); }
@@ -250,8 +286,25 @@ template <typename C, int N> struct XchgContigSw {
         if (N / 16 <= 32) __syncwarp(); else __syncthreads();
     }
 };
+// Contiguous lines, real and imaginary parts crossing one after the other (fft_stage_v, SPLIT): the
+// line's slice holds N padded REALS -- half the shared memory of XchgContig (35 instead of 70 KB for
+// the 8 lines of a 512-point tile) for twice the 8-byte accesses.  LS is in units of C.
+template <typename C, int N> struct XchgContigSplit {
+    static constexpr bool SPLIT = true;
+    using R = decltype(C::x);
+    R* base;
+    static constexpr int LS = (N + N / 16) / 2;
+    __device__ __forceinline__ R ldx(int i) const { return base[i + (i >> 4)]; }
+    __device__ __forceinline__ void stx(int i, R v) const { base[i + (i >> 4)] = v; }
+    __device__ __forceinline__ C ld(int i) const { return C(); }          // (never taken: SPLIT stages use ldx / stx)
+    __device__ __forceinline__ void st(int, C) const {}
+    __device__ __forceinline__ void sync() const {
+        if (N / 16 <= 32) __syncwarp(); else __syncthreads();
+    }
+};
 // Strided lines (y or x axis): W adjacent lines per CTA, lane index = column.
 template <typename C, int W> struct XchgStrided {
+    static constexpr bool SPLIT = false;
     C* base;            // buffer + column
     __device__ __forceinline__ C ld(int i) const { return base[i * W]; }
     __device__ __forceinline__ void st(int i, C v) const { base[i * W] = v; }

@@ -31,6 +31,7 @@ struct FusedParams {
     unsigned* ticket;           // one counter
     unsigned* zdone;            // [nx]
     unsigned* ydone;            // [nx]
+    unsigned* pair;             // [nx][yt/2]: finished y tiles per tile pair (tiles narrower than a 128-byte line share the discard)
     int lead;                   // planes the z role runs ahead of the y role
     int ring;                   // scratch planes (ring > lead; ring >= nx: no wrap)
     int zt, yt;                 // tiles per plane of each role
@@ -71,10 +72,12 @@ __device__ __forceinline__ void signal_counter(unsigned* ctr) {
 // tables come transposed from global memory (twt = [forward stage | inverse stage]).
 // ZM = 0: tables from global memory (L1), unpadded swizzled exchange (64 KB of shared memory);
 // ZM = 1: k_zline's layout -- stage tables + multiplier copied to shared memory, padded exchange.
+// ZM = 2: as 1 with the split real / imaginary exchange (XchgContigSplit): 64 instead of 98 KB at N = 512,
+//         below the y role's 80 KB, so the CTA pair leaves 90 KB of L1 to the streaming phase.
 template <int N, int ZM> struct FusedZSmem {
     using TT_ = TwTables<N, 16>;
-    static constexpr int TABLES = (ZM == 1) ? ((TT_::NEED_MASTER ? N : 0) + (TT_::SHARED ? 0 : TT_::FWD) + TT_::INV + N) : 0;
-    static constexpr int LS = (ZM == 1) ? (N + N / 16) : N;
+    static constexpr int TABLES = (ZM >= 1) ? ((TT_::NEED_MASTER ? N : 0) + (TT_::SHARED ? 0 : TT_::FWD) + TT_::INV + N) : 0;
+    static constexpr int LS = (ZM == 2) ? (N + N / 16) / 2 : ((ZM == 1) ? (N + N / 16) : N);
     static constexpr int ELEMS = TABLES + ZCfg<N, 16>::LPB * LS;      // complex elements
 };
 
@@ -89,14 +92,15 @@ __device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedPara
                                              const typename Cx<T>::type* __restrict__ ml) {
     using C = typename Cx<T>::type;
     using F = Fld<T, CPLX>;
-    using X = typename std::conditional<ZM == 1, XchgContig<C, N>, XchgContigSw<C, N>>::type;
+    using X = typename std::conditional<ZM == 2, XchgContigSplit<C, N>,
+                  typename std::conditional<ZM == 1, XchgContig<C, N>, XchgContigSw<C, N>>::type>::type;
     using TT_ = TwTables<N, 16>;
     constexpr bool TWT = N > 16;
     constexpr int TT = ZCfg<N, 16>::TT, LPB = ZCfg<N, 16>::LPB;
     const C* twf = twt;
     const C* twi = TT_::SHARED ? twt : twt + TT_::FWD;
     C* xbuf = smem;
-    if constexpr (ZM == 1) {
+    if constexpr (ZM >= 1) {
         C* s_tw = smem;
         C* s_twf = s_tw + (TT_::NEED_MASTER ? N : 0);
         C* s_twi = TT_::SHARED ? s_twf : s_twf + TT_::FWD;
@@ -114,7 +118,7 @@ __device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedPara
         tw = s_tw; twf = s_twf; twi = s_twi; ml = s_ml;
     }
     const int t = threadIdx.x % TT, l = threadIdx.x / TT;
-    X xb{xbuf + (size_t)l * X::LS};
+    X xb{reinterpret_cast<decltype(X::base)>(xbuf + (size_t)l * X::LS)};
     long long t0 = fp.prof ? clock64() : 0;
     // Experiment (option fused_prefetch, off): the z role asks L2 for the rows of F_z and the three G
     // arrays its plane's y tiles will stream `lead` planes later.  Measured: y update phase 17.7 k ->
@@ -215,6 +219,23 @@ k_shpf_fused(const UpdParams p, const FusedParams fp,
         const long long plane = (long long)p.ny * p.nz;
         const long long dz_off = ((long long)(i % fp.ring) - (long long)i) * plane;
         yline_phase_b_dispatch<T, CPLX, NY, false, true>(p, i, kb, fp.yt, xbuf, dz_off);
+        if constexpr (YCfg<T, CPLX, NY>::W * sizeof(T) == 64) {
+            // 8-column tiles (N = 512): a 128-byte scratch line belongs to two adjacent tiles; the one that
+            // finishes second drops the pair's lines from L2 (see yline_phase_b for the wide-tile case)
+            if (p.dz_discard) {
+                __syncthreads();                    // this tile's loads are consumed
+                if (threadIdx.x == 0) s_ticket = atomicAdd(fp.pair + (size_t)(i - p.i0) * (fp.yt / 2) + kb / 2, 1u);
+                __syncthreads();
+                const int k = (kb & ~1) * YCfg<T, CPLX, NY>::W;
+                if (s_ticket == 1u && k >= p.dz_keep_lo && k + 16 <= p.dz_keep_hi) {
+                    for (int j = (int)threadIdx.x; j < p.ny; j += (int)blockDim.x) {
+                        const size_t e = (size_t)((long long)i * plane + (long long)j * p.nz + k + dz_off);
+                        asm volatile("discard.global.L2 [%0], 128;" :: "l"((const T*)p.dz[0] + e) : "memory");
+                        asm volatile("discard.global.L2 [%0], 128;" :: "l"((const T*)p.dz[1] + e) : "memory");
+                    }
+                }
+            }
+        }
         // only a z tile that re-uses this plane's ring slot waits for it
         if (i + fp.ring < p.i1) signal_counter(fp.ydone + i);
         fprof(fp, 5, &t0);
@@ -241,15 +262,18 @@ int launch_shpf_fused(Ctx* c, const UpdParams& p, int half) {
         fp.prefetch = c->fused_prefetch;
         // (measured alternative: counters that only grow, target = tiles x launch number, no memset --
         //  0.8% SLOWER on the headline in a same-box A/B of the two builds, 2.923 vs 2.895 ms; kept the memset)
-        IES_CUDA(cudaMemsetAsync(c->fused_sync, 0, sizeof(unsigned) * (size_t)(1 + 2 * c->cfg.nx), c->stream));
+        fp.pair = c->fused_sync + 1 + 2 * c->cfg.nx;
+        const bool pairs = p.dz_discard && ny == 512;
+        IES_CUDA(cudaMemsetAsync(c->fused_sync, 0, sizeof(unsigned) * (size_t)(1 + 2 * c->cfg.nx + (pairs ? 32 * c->cfg.nx : 0)), c->stream));
         const int nplanes = p.i1 - p.i0;
 #define F_CASE(NN) {                                                                        \
             fp.zt = (ny + ZCfg<NN, 16>::LPB - 1) / ZCfg<NN, 16>::LPB;                       \
             fp.yt = (nz + YCfg<T, CPLX, NN>::W - 1) / YCfg<T, CPLX, NN>::W;                  \
             const size_t sm0 = sizeof(C) * (size_t)NN * YCfg<T, CPLX, NN>::W;                \
-            const size_t sm = std::max(sizeof(C) * (size_t)FusedZSmem<NN, 1>::ELEMS, sm0 + sizeof(C) * 2 * NN); \
+            constexpr int ZM_ = (NN == 512) ? 2 : 1;                                        \
+            const size_t sm = std::max(sizeof(C) * (size_t)FusedZSmem<NN, ZM_>::ELEMS, sm0 + sizeof(C) * 2 * NN); \
             const bool z2 = c->fused_zb == 2 && fp.zt % 2 == 0;                            \
-            auto kern = z2 ? k_shpf_fused<T, CPLX, NN, NN, 1, 1, 2> : k_shpf_fused<T, CPLX, NN, NN, 1, 1, 1>; \
+            auto kern = z2 ? k_shpf_fused<T, CPLX, NN, NN, ZM_, 1, 2> : k_shpf_fused<T, CPLX, NN, NN, ZM_, 1, 1>; \
             if (set_smem(kern, sm)) return 1;                                               \
             const unsigned grid = (unsigned)((nplanes + fp.lead) * (fp.zt / (z2 ? 2 : 1) + fp.yt)); \
             kern<<<grid, 256, sm, c->stream>>>(p, fp, (const C*)c->tw[1], (const C*)c->mult[half][1], \

@@ -62,6 +62,12 @@ template <int N, int VPT> struct ZCfg {
 };
 template <typename C, int N, int VPT> struct ZXchg { using type = XchgContig<C, N>; };
 template <typename C, int N> struct ZXchg<C, N, 8> { using type = XchgContig8<C, N>; };
+// 512-point z lines cross threads with the split real / imaginary exchange: 64 instead of 98 KB of shared memory
+// per CTA (two CTAs per SM by registers either way: 100 KB more L1 for the streaming loads / stores); Mie slab 4.30 -> 4.19 ms/step
+// (same-box A/B of two builds, tools/gpu_call_r2i.sh).  -DIES_Z512_NOSPLIT restores the padded complex exchange.
+#ifndef IES_Z512_NOSPLIT
+template <typename C> struct ZXchg<C, 512, 16> { using type = XchgContigSplit<C, 512>; };
+#endif
 
 // One CTA = LPB adjacent z lines.  Input lines start at line0 (+ blockIdx.x*LPB), the
 // derivative lines go to oline0 (+ blockIdx.x*LPB) of the scratch arrays.  VPT = register
@@ -103,7 +109,7 @@ k_zline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
     const bool ok = line < nlines;
     const size_t ibase = (size_t)(line0 + line) * N;
     const size_t obase = (size_t)(oline0 + line) * N;
-    X xb{xbuf + (size_t)l * X::LS};
+    X xb{reinterpret_cast<decltype(X::base)>(xbuf + (size_t)l * X::LS)};
 #pragma unroll 1
     for (int f = 0; f < F::NF; ++f) {
         C v[VPT];
@@ -299,11 +305,11 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
             // ld.cs / L1::no_allocate / ld.cg on the streaming operands cost 8-13 %)
 #pragma unroll
             for (int c = 0; c < 3; ++c) vst_stream<VV>(p.G[c], idx, g[u][c], 0);
-            if constexpr (DISC && !CPLX && sizeof(T) == 8) {
+            if constexpr (DISC && !CPLX && sizeof(T) == 8 && W % 16 == 0) {      // (W = 8 at N = 512: a line spans two tiles)
                 // fused kernel: this tile was the only reader of its z-derivative scratch lines (a row segment of
                 // the tile is whole 128-byte lines, read by lanes of this warp in the load above): drop them from
-                // L2 so the dirty lines are never written back to HBM
-                if (p.dz_discard && (cg * V) % 16 == 0) {
+                // L2 so the dirty lines are never written back to HBM (lines the CPML pass still reads are kept)
+                if (p.dz_discard && (cg * V) % 16 == 0 && k >= p.dz_keep_lo && k + 16 <= p.dz_keep_hi) {
                     const size_t e = (size_t)((long long)idx + dz_off);
                     asm volatile("discard.global.L2 [%0], 128;" :: "l"((const double*)p.dz[0] + e) : "memory");
                     asm volatile("discard.global.L2 [%0], 128;" :: "l"((const double*)p.dz[1] + e) : "memory");

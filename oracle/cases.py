@@ -107,6 +107,9 @@ LIVE_CASES = [
     _case('shpf_f64_z512_y128', 'SHPF', 'float64', (12, 128, 512), steps=6, npml=4, pbc=PBC_YZ, bbc=NO, src='point'),
     _case('shpf_f64_y512_z32', 'SHPF', 'float64', (12, 512, 32), steps=6, npml=4, pml=ALLPML, src='point'),
     _case('shpf_c64_z512_y16', 'SHPF', 'complex64', (12, 16, 512), steps=6, npml=4, pbc=PBC_YZ, bbc=NO, src='point'),
+    # the split real / imaginary exchange of the 512-point z lines for the other element types
+    _case('shpf_f32_z512_y32', 'SHPF', 'float32', (12, 32, 512), steps=6, npml=4, pml=ALLPML, src='point'),
+    _case('shpf_c128_z512_y16', 'SHPF', 'complex128', (12, 16, 512), steps=4, npml=3, bbc=BBC_YZ, pbc=NO, mmt=K1, src='point'),
     # spectral axes that are not a power of two (the reference takes any N; the engine applies the derivative
     # as a circulant sum there): the shipped 50^3 set-up's line length, mixed lengths, complex odd lengths
     _case('shpf_f64_50cube', 'SHPF', 'float64', (30, 50, 50), steps=8, npml=4, pbc=PBC_YZ, bbc=NO),
