@@ -13,8 +13,8 @@ def main(path, top=30):
     cur = None
     for r in rows:
         if not r: continue
-        if r[0] == 'File Name': fname = r[1].split('/')[-1]; continue
-        if r[0] == 'Kernel Name': continue
+        if r[0] in ('File Name', 'File Path'): fname = r[1].split('/')[-1]; continue
+        if r[0] in ('Kernel Name', 'Function Name'): continue
         if r[0] == 'Line No': hdr = r; continue
         if hdr is None or len(r) < len(hdr) - 2: continue
         if r[0] != '':                       # a CUDA source line; its SASS rows follow with an empty first column
