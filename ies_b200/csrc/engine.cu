@@ -1040,7 +1040,7 @@ int ies_set_option(ies_ctx* c, const char* name, int64_t value) {
     else if (n == "pml_split") c->use_pml_split = v;
     else if (n == "fused") c->use_fused = v;
     else if (n == "fused_lead") c->fused_lead = v < 1 ? 1 : v;
-    else if (n == "fused_zb") c->fused_zb = v == 2 ? 2 : 1;
+    else if (n == "fused_zb") c->fused_zb = v >= 4 ? 4 : v >= 2 ? 2 : 1;
     else if (n == "fused_prefetch") c->fused_prefetch = v;
     else if (n == "fused_discard") c->fused_discard = v;
     else if (n == "fused_ring") c->fused_ring_planes = v;

@@ -109,7 +109,7 @@ struct Ctx {
     int use_fused;                     // 1 = k_shpf_fused where instantiated, 0 = k_zline + k_yline_update
     int fused_prefetch;                // z role prefetches F_z and G of its rows into L2 for the y role
     int fused_discard;                 // y role discards the dz scratch lines it consumed (no DRAM write-back of the scratch)
-    int fused_zb;                      // z tiles per z-role CTA (1 or 2)
+    int fused_zb;                      // z tiles per z-role CTA (1, 2 or 4)
     int fused_lead, fused_ring_planes; // planes of lead of the z role; scratch ring size in planes
     unsigned* fused_sync;              // ticket + zdone[nx] + ydone[nx]
     void* fused_ring[2];               // ring scratch (fused_ring_planes planes each) or null

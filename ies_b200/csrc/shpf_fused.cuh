@@ -100,6 +100,24 @@ __device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedPara
     const C* twf = twt;
     const C* twi = TT_::SHARED ? twt : twt + TT_::FWD;
     C* xbuf = smem;
+    const int t = threadIdx.x % TT, l = threadIdx.x / TT;
+    // The first tile's field loads are issued BEFORE the tables are staged, so that the two global round
+    // trips (tables, fields) overlap instead of following each other across the staging barrier.
+    C v[F::NF][16];
+    auto load_tile = [&](const int zb) {
+        const int row = (tile0 + zb) * LPB + l;
+        const size_t ibase = ((size_t)pz * p.ny + row) * N;
+#pragma unroll
+        for (int f = 0; f < F::NF; ++f) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (row < p.ny) v[f][q] = F::ld(p.F[1], p.F[0], ibase + line_index_v<N, 16>(t, q), f);
+                else { v[f][q].x = 0; v[f][q].y = 0; }
+            }
+        }
+    };
+    constexpr bool PRELOAD = F::NF == 1;
+    if constexpr (PRELOAD) load_tile(0);
     if constexpr (ZM >= 1) {
         C* s_tw = smem;
         C* s_twf = s_tw + (TT_::NEED_MASTER ? N : 0);
@@ -117,7 +135,6 @@ __device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedPara
         __syncthreads();
         tw = s_tw; twf = s_twf; twi = s_twi; ml = s_ml;
     }
-    const int t = threadIdx.x % TT, l = threadIdx.x / TT;
     X xb{reinterpret_cast<decltype(X::base)>(xbuf + (size_t)l * X::LS)};
     long long t0 = fp.prof ? clock64() : 0;
     // Experiment (option fused_prefetch, off): the z role asks L2 for the rows of F_z and the three G
@@ -138,16 +155,10 @@ __device__ __forceinline__ void fused_z_role(const UpdParams& p, const FusedPara
     for (int zb = 0; zb < ZB; ++zb) {
     const int row = (tile0 + zb) * LPB + l;
     const bool ok = row < p.ny;
-    const size_t ibase = ((size_t)pz * p.ny + row) * N;
     const size_t obase = ((size_t)(pz % fp.ring) * p.ny + row) * N;
-    C v[F::NF][16];
+    if (!PRELOAD || zb > 0) load_tile(zb);
 #pragma unroll
     for (int f = 0; f < F::NF; ++f) {
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            if (ok) v[f][q] = F::ld(p.F[1], p.F[0], ibase + line_index_v<N, 16>(t, q), f);
-            else { v[f][q].x = 0; v[f][q].y = 0; }
-        }
         fft_forward_v<N, 16, TWT>(v[f], t, tw, xb, twf);
 #pragma unroll
         for (int q = 0; q < 16; ++q) v[f][q] = cmul(v[f][q], ml[spec_index_v<N, 16>(t, q)]);
@@ -272,10 +283,11 @@ int launch_shpf_fused(Ctx* c, const UpdParams& p, int half) {
             const size_t sm0 = sizeof(C) * (size_t)NN * YCfg<T, CPLX, NN>::W;                \
             constexpr int ZM_ = (NN == 512) ? 2 : 1;                                        \
             const size_t sm = std::max(sizeof(C) * (size_t)FusedZSmem<NN, ZM_>::ELEMS, sm0 + sizeof(C) * 2 * NN); \
-            const bool z2 = c->fused_zb == 2 && fp.zt % 2 == 0;                            \
-            auto kern = z2 ? k_shpf_fused<T, CPLX, NN, NN, ZM_, 1, 2> : k_shpf_fused<T, CPLX, NN, NN, ZM_, 1, 1>; \
+            const int zb = (c->fused_zb == 4 && fp.zt % 4 == 0) ? 4 : (c->fused_zb >= 2 && fp.zt % 2 == 0) ? 2 : 1; \
+            auto kern = zb == 4 ? k_shpf_fused<T, CPLX, NN, NN, ZM_, 1, 4> : zb == 2 ? k_shpf_fused<T, CPLX, NN, NN, ZM_, 1, 2> \
+                                                                             : k_shpf_fused<T, CPLX, NN, NN, ZM_, 1, 1>; \
             if (set_smem(kern, sm)) return 1;                                               \
-            const unsigned grid = (unsigned)((nplanes + fp.lead) * (fp.zt / (z2 ? 2 : 1) + fp.yt)); \
+            const unsigned grid = (unsigned)((nplanes + fp.lead) * (fp.zt / zb + fp.yt));          \
             kern<<<grid, 256, sm, c->stream>>>(p, fp, (const C*)c->tw[1], (const C*)c->mult[half][1], \
                 (const C*)c->tw[2], (const C*)c->twz_t, (const C*)c->mult[half][2]);        \
         }

@@ -192,6 +192,18 @@ k_xline(const void* __restrict__ A, const void* __restrict__ B, void* __restrict
 }
 
 // ------------------------------------------ y lines + fused field update -----
+// Column -> slot of a y tile's shared-memory rows (exchange buffer and derivative stash).  fp64 real tiles
+// are 16+ columns of 16-byte pairs; phase A has lane = column (a quarter-warp = columns 0..7 or 8..15), phase B
+// has lane = column PAIR (a quarter-warp = the even or the odd columns of one row), and a 16-byte access is
+// conflict free when its quarter-warp covers the eight 16-byte bank groups.  Swapping neighbours in every second
+// group of eight columns, c ^ ((c >> 3) & 1), satisfies both (the identity gave phase B a 2-way conflict on every stash read:
+// 16.8 M of 284 M shared wavefronts per launch in the ncu capture of the headline).
+template <typename T, bool CPLX, int W>
+__device__ __forceinline__ int stash_col(const int c) {
+    if constexpr (!CPLX && sizeof(T) == 8 && W >= 16) return c ^ ((c >> 3) & 1);
+    else return c;
+}
+
 // Phase B of k_yline_update.  FAST: no CPML term touches the tile and every update box either
 // contains or misses it (upd = component mask, CTA-uniform): straight-line interior code.
 // CM: where the coefficient comes from -- 0 the f64 array, 1 the palette form, 2 one value for
@@ -268,9 +280,9 @@ __device__ __forceinline__ void yline_phase_b(const UpdParams& p, const int i, c
 #pragma unroll
                 for (int v = 0; v < V; ++v) {
                     A d[6];
-                    const C r0 = xbuf[(size_t)j * W + cg * V + v];
+                    const C r0 = xbuf[(size_t)j * W + stash_col<T, CPLX, W>(cg * V + v)];
                     if constexpr (CPLX) {
-                        const C r1 = xbuf[(size_t)N * W + (size_t)j * W + cg * V + v];
+                        const C r1 = xbuf[(size_t)N * W + (size_t)j * W + stash_col<T, CPLX, W>(cg * V + v)];
                         d[0] = make_double2((double)r0.x, (double)r0.y);
                         d[5] = make_double2((double)r1.x, (double)r1.y);
                     } else {
@@ -349,7 +361,7 @@ __device__ __forceinline__ void yline_phase_a(const UpdParams& p, const int i, c
     // pair (F_z, F_x): Re -> d/dy F_z (slot 0), Im -> d/dy F_x (slot 5)
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
-        XchgStrided<C, W> xb{xbuf + (size_t)f * N * W + c};
+        XchgStrided<C, W> xb{xbuf + (size_t)f * N * W + stash_col<T, CPLX, W>(c)};
         C v[16];
 #pragma unroll
         for (int q = 0; q < 16; ++q) {

@@ -80,7 +80,7 @@ int ies_sync(ies_ctx* ctx);
  *               y-line tiles as two roles of one grid [shpf_fused.cuh]; 0 = z-line derivative kernel +
  *               y-line update kernel; -1 [default] = fused where it is faster (fp64, lines <= 256 points);
  *  "fused_lead" planes the z role runs ahead (6); "fused_ring" scratch ring size in planes (0 = full-size
- *               scratch); "fused_zb" z tiles per z-role CTA (2); "fused_prefetch" (0); "fused_discard" 1 [default] =
+ *               scratch); "fused_zb" z tiles per z-role CTA (1, 2 [default] or 4); "fused_prefetch" (0); "fused_discard" 1 [default] =
  *               a y tile drops the z-derivative scratch lines it has consumed from L2 (discard.global.L2), so
  *               the dirty scratch is never written back to HBM;
  *  "pml_split"  CPML corrections: 1 = a separate pass over the absorber cells after the update kernels
